@@ -1,0 +1,276 @@
+/*
+ * lolb200.h -- C ABI of the B200 (sm_100a) sphere-tracing backend for loltracer.
+ *
+ * Plain C: pointers, sizes and PODs only; no CUDA, torch or SDL type crosses this
+ * boundary.  Every entry point names the reference interface it stands in for
+ * (paths relative to the reference tree, iglosiggio/loltracer).
+ *
+ * Layering (bottom-up):
+ *   1. scene description  (PODs mirroring scene.h:44-96, flattened: no pointers
+ *                          into the reference's `struct vector`)
+ *   2. .lol front-end     (replaces scene_parse(), scene-parser.y:197-214)
+ *   3. lowering           (scene -> specialised CUDA C; replaces generate_sdf(),
+ *                          tracing_jit_renderer.dasc:76-143)
+ *   4. device layer       (NVRTC sm_100a + launch; replaces link_and_encode(),
+ *                          tracing_jit_renderer.dasc:60-74, and the pixel loop of
+ *                          render_thread(), naive_renderer.c:195-240)
+ *
+ * The renderer.h drop-in itself (render_thread / render_prepare / render_destroy,
+ * renderer.h:24-26) lives in loltracer_b200/backend/b200_renderer.c and is built
+ * on this ABI only.
+ *
+ * Error convention: functions returning int return 0 on success and a negative
+ * LOLB200_E* code on failure; lolb200_last_error() gives the message for the
+ * calling thread.  There is no CPU fallback anywhere: device functions fail with
+ * LOLB200_ENODEVICE when no CUDA device is usable.
+ */
+#ifndef LOLB200_H
+#define LOLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOLB200_ABI_VERSION 1
+
+enum {
+	LOLB200_OK = 0,
+	LOLB200_EPARSE = -1,    /* .lol syntax / semantic error                    */
+	LOLB200_EINVAL = -2,    /* bad argument                                    */
+	LOLB200_ENODEVICE = -3, /* no usable CUDA device / driver                  */
+	LOLB200_ECOMPILE = -4,  /* NVRTC rejected the generated source             */
+	LOLB200_ECUDA = -5,     /* a CUDA call failed                              */
+	LOLB200_ENOMEM = -6
+};
+
+/* ---------------------------------------------------------------- 1. scene -- */
+
+/* Values equal enum components in scene.h:27-35 so a reference `struct object`
+ * translates with a plain copy of `type`. */
+enum lolb200_object_type {
+	LOLB200_OBJ_SPHERE = 3,
+	LOLB200_OBJ_BOX = 4,
+	LOLB200_OBJ_PLANE = 5,
+	LOLB200_OBJ_SMOOTH_UNION = 6
+};
+
+/* scene.h:44-49 */
+typedef struct lolb200_material {
+	float shininess;
+	float diffuse[3];
+	float specular[3];
+	float ambient[3];
+} lolb200_material;
+
+/* scene.h:52-56 */
+typedef struct lolb200_light {
+	float point[3];
+	float diffuse_intensity[3];
+	float specular_intensity[3];
+} lolb200_light;
+
+/* scene.h:58-82.  Children of a smooth union are indices into the node array
+ * (the reference holds malloc'ed pointers, scene.c:18-29). */
+typedef struct lolb200_object {
+	int32_t type;      /* enum lolb200_object_type                        */
+	uint32_t material; /* only read for top-level objects (naive_renderer.c:102-112) */
+	float point[3];    /* plane: (0, y, 0) as scene.c:215                 */
+	float radius;      /* sphere radius / box rounding radius             */
+	float point2[3];   /* box half extents                                */
+	float smoothness;  /* smooth union k                                  */
+	int32_t a, b;      /* smooth union children (node indices), else -1   */
+} lolb200_object;
+
+/* scene.h:84-88.  direction is unit length and fov is in radians, exactly as
+ * camera_from_definition_list leaves them (scene.c:173-174). */
+typedef struct lolb200_camera {
+	float point[3];
+	float direction[3];
+	float fov;
+} lolb200_camera;
+
+/* scene.h:90-96, flattened.  `objects[i]` is the node index of top-level object
+ * with id i+1 (id 0 = nothing, naive_renderer.c:30-44). */
+typedef struct lolb200_scene {
+	uint32_t n_materials;
+	lolb200_material* materials;
+	float ambient_color[3];
+	uint32_t n_lights;
+	lolb200_light* lights;
+	uint32_t n_nodes;
+	lolb200_object* nodes;
+	uint32_t n_objects;
+	uint32_t* objects;
+	lolb200_camera camera;
+} lolb200_scene;
+
+/* ------------------------------------------------------------ 2. front-end -- */
+
+/* Replaces scene_parse() (scene-parser.y:197-214) + the property extractors of
+ * scene.c:140-281 + scene_validate_materials() (scene.c:284-292, main.c:235).
+ * Accepts exactly the token set of scene-lexer.l:10-50 and the grammar of
+ * scene-parser.y:73-189.  Where the reference calls exit(1)/assert (unknown
+ * property, wrong value type, bad material index) this returns LOLB200_EPARSE. */
+int lolb200_scene_parse_file(const char* path, lolb200_scene** out);
+int lolb200_scene_parse_string(const char* text, size_t len, lolb200_scene** out);
+/* Deep copy / free (scene_free(), scene.c:60-65). */
+lolb200_scene* lolb200_scene_clone(const lolb200_scene* s);
+void lolb200_scene_free(lolb200_scene* s);
+
+/* Camera basis exactly as get_camera_ray() derives it per pixel
+ * (naive_renderer.c:178-193), hoisted to once per frame: this is the only place
+ * the path calls atanf, so it stays on the host (glibc) for parity.
+ * rd(x,y) = normalize((right*(vx*width) + up*(vy*height)) + dir). */
+typedef struct lolb200_camera_basis {
+	float origin[3];
+	float dir[3];
+	float right[3];
+	float up[3];
+	float width;  /* aspect * atanf(fov/2)  */
+	float height; /* atanf(fov/2)           */
+} lolb200_camera_basis;
+void lolb200_camera_basis_compute(const lolb200_camera* cam, int w, int h,
+                                  lolb200_camera_basis* out);
+
+/* ------------------------------------------------------------- 3. lowering -- */
+
+enum lolb200_arith {
+	/* Operation order and rounding of the reference (no FMA contraction, IEEE
+	 * div/sqrt, MINSS/MAXSS NaN rules): the parity mode. */
+	LOLB200_ARITH_EXACT = 0,
+	/* --fmad=true, reciprocal multiplies, FMNMX min/max: not bit-faithful. */
+	LOLB200_ARITH_FAST = 1
+};
+
+typedef struct lolb200_options {
+	int32_t arith;           /* enum lolb200_arith                              */
+	int32_t skip_black_miss; /* 1: allow the exact miss-pixel shortcut when
+	                            material 0 is all-zero; 0: always shade misses  */
+	int32_t cull_backfacing; /* 1: skip a light's shadow march when n.l <= 0
+	                            (its contribution is exactly +0)                */
+	int32_t shadow_early_out;/* 1: leave the shadow march once res <= 0 (the
+	                            returned value is then exactly 0)               */
+	int32_t counters;        /* 1: kernel also accumulates per-phase SDF
+	                            evaluation counts (instrumented build)          */
+	int32_t variant;         /* kernel structure: 0 = default for this build,
+	                            1 = phase-sequential, 2 = megaloop + lane refill */
+	int32_t loop_threshold;  /* top-level runs of >= this many same-shape
+	                            objects become a loop over __constant__ tables;
+	                            0 = default (16)                                */
+	int32_t reserved[9];
+} lolb200_options;
+void lolb200_options_default(lolb200_options* o);
+
+/* Replaces generate_sdf()/generate_obj_dist() (tracing_jit_renderer.dasc:76-216):
+ * emits CUDA C with every scene constant baked in.  Pure host code, no device
+ * needed.  Returns a malloc'ed NUL-terminated string (free with lolb200_free). */
+char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* o, size_t* len);
+void lolb200_free(void* p);
+
+/* Algorithmic FLOPs of one sdf() evaluation with the convention of DESIGN.md
+ * (sphere 10, round box 20, plane 1, smooth node 13, +1 per top-level object). */
+uint64_t lolb200_scene_flops_per_eval(const lolb200_scene* s);
+
+/* ---------------------------------------------------------- 4. device layer -- */
+
+/* NVRTC for sm_100a; works without a GPU (cross-compile).  Replaces
+ * link_and_encode() (tracing_jit_renderer.dasc:60-74).  *image is malloc'ed. */
+int lolb200_compile_cubin(const char* cuda_src, const lolb200_options* o,
+                          void** image, size_t* image_size, char** log);
+
+int lolb200_device_count(void);
+
+typedef struct lolb200_renderer lolb200_renderer; /* opaque */
+
+/* render_prepare() analogue (tracing_jit_renderer.dasc:416-434): lower, compile,
+ * load the module on `device`, allocate the work counter. */
+int lolb200_renderer_create(const lolb200_scene* s, const lolb200_options* o,
+                            int device, lolb200_renderer** out);
+/* render_destroy() analogue. */
+void lolb200_renderer_destroy(lolb200_renderer* r);
+/* Generated source / SASS-bearing image, the analogue of `--jitdump`
+ * (tracing_jit_renderer.dasc:424-433, jitdump.c:93-120). */
+const char* lolb200_renderer_source(const lolb200_renderer* r);
+const void* lolb200_renderer_image(const lolb200_renderer* r, size_t* size);
+int lolb200_renderer_kernel_info(const lolb200_renderer* r, int* regs, int* smem_bytes,
+                                 int* local_bytes, int* max_threads);
+
+/* How 32-bit pixels are packed: what SDL_MapRGB(surf->format, r, g, b) does for
+ * a non-palettised 32-bit format (renderer.h:17-22). */
+typedef struct lolb200_pixfmt {
+	uint8_t rshift, gshift, bshift;
+	uint8_t rloss, gloss, bloss;
+	uint16_t pad;
+	uint32_t amask; /* OR-ed into every pixel */
+} lolb200_pixfmt;
+/* XRGB8888 with alpha forced to 0xFF: 0xFF000000 | r<<16 | g<<8 | b. */
+void lolb200_pixfmt_default(lolb200_pixfmt* f);
+
+/* Which rows of the frame this launch renders.  Row band b (band_rows rows)
+ * belongs to rank b % world; a rank stores its bands compactly, band after band
+ * ([local_band][band_rows][W] pixels), or -- with dst_full_frame -- at their
+ * final position in a full W x H frame (its own or a peer-mapped one). */
+typedef struct lolb200_shard {
+	int32_t rank, world;
+	int32_t band_rows;      /* multiple of 4; 0 = default (4)                  */
+	int32_t dst_full_frame; /* 0: compact local buffer, 1: full-frame indexing */
+} lolb200_shard;
+
+/* Optional per-pixel auxiliaries for parity tests (not part of the product
+ * frame): final march distance, object id (0 = miss), primary step count and
+ * total shadow-march evaluations.  Any pointer may be NULL. Full-frame indexed. */
+typedef struct lolb200_aux {
+	float* dist;
+	uint32_t* id;
+	uint16_t* primary_steps;
+	uint16_t* shadow_steps;
+} lolb200_aux;
+
+/* The pixel loop of render_thread() (naive_renderer.c:216-236) for one frame or
+ * one shard of it, asynchronously on `stream` (a cudaStream_t passed as void*,
+ * NULL = default stream).  dst_dev is DEVICE memory, pitch_px in pixels. */
+int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                          const lolb200_pixfmt* fmt, const lolb200_shard* shard,
+                          void* dst_dev, size_t pitch_px, const lolb200_aux* aux_dev,
+                          void* stream);
+
+/* Same, end to end for a host surface (surf->pixels, surf->pitch in BYTES):
+ * uploads the camera, renders on the renderer's device, copies the frame into
+ * `pixels` honouring `pitch_bytes`, and returns when the pixels are visible to
+ * the host.  This is what b200_renderer.c's frame leader calls. */
+int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                        const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes);
+
+/* Sum of the instrumented counters since the last call (options.counters = 1):
+ * [0] primary evals, [1] normal-tap evals, [2] shadow evals, [3] pixels,
+ * [4] hit pixels, [5] shadow rays marched, [6] shadow rays culled. */
+int lolb200_read_counters(lolb200_renderer* r, uint64_t out[8]);
+
+/* Rank 0's de-interleave after a gather: `gathered` holds world compact shards
+ * back to back (each padded to shard_pixels), `frame` is the W x H result. */
+int lolb200_deinterleave_device(const void* gathered_dev, void* frame_dev, int w, int h,
+                                int world, int band_rows, size_t shard_pixels,
+                                size_t pitch_px, void* stream);
+/* Pixels a rank's compact buffer needs (bands padded so every rank is equal). */
+size_t lolb200_shard_pixels(int w, int h, int world, int band_rows);
+
+/* CUDA-IPC plumbing for the peer-store variant (render fused with its gather):
+ * export a 64-byte handle for a device allocation / map a peer's handle. */
+int lolb200_ipc_export(void* dev_ptr, uint8_t handle[64]);
+int lolb200_ipc_open(const uint8_t handle[64], void** dev_ptr);
+int lolb200_ipc_close(void* dev_ptr);
+
+/* Independent-chain FFMA microbenchmark: the measured FP32 denominator that
+ * MEASURED_PEAKS.json lacks.  Returns TFLOP/s (2 FLOP per FFMA), <0 on error. */
+double lolb200_measure_fp32_peak(int device, int iters, double* ms_out);
+
+const char* lolb200_last_error(void);
+int lolb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOLB200_H */
