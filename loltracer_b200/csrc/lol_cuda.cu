@@ -1,0 +1,584 @@
+/*
+ * lol_cuda.cu -- the thin C-ABI CUDA layer of liblolb200 (sm_100a only).
+ *
+ * Host side: NVRTC (sm_100a) -> cudaLibrary -> persistent launch of the
+ * per-scene kernel; frame plumbing (shards, de-interleave, host read-back).
+ * The analogue of link_and_encode()/render_prepare() in
+ * tracing_jit_renderer.dasc:60-74,416-434: there the code lands in an mmap'ed
+ * RX page, here in a CUDA module.
+ *
+ * Static kernels in this file: the de-interleave after a gather and the FFMA
+ * microbenchmark that supplies the FP32 roofline denominator.
+ *
+ * There is no CPU fallback: every device entry point fails with
+ * LOLB200_ENODEVICE / LOLB200_ECUDA when the GPU is not usable.
+ */
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lol_internal.h"
+#include "lol_params.h"
+#include "lolb200.h"
+
+#define CUDA_TRY(expr)                                                                   \
+	do {                                                                                 \
+		cudaError_t e_ = (expr);                                                         \
+		if (e_ != cudaSuccess) {                                                         \
+			lolb200_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+			                  __FILE__, __LINE__);                                       \
+			return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver)        \
+			           ? LOLB200_ENODEVICE                                               \
+			           : LOLB200_ECUDA;                                                  \
+		}                                                                                \
+	} while (0)
+
+namespace {
+
+struct DeviceGuard {
+	int prev = -1;
+	bool ok = false;
+	explicit DeviceGuard(int dev) {
+		if (cudaGetDevice(&prev) != cudaSuccess)
+			prev = -1;
+		ok = cudaSetDevice(dev) == cudaSuccess;
+	}
+	~DeviceGuard() {
+		if (prev >= 0)
+			cudaSetDevice(prev);
+	}
+};
+
+} // namespace
+
+struct lolb200_renderer {
+	int device = 0;
+	lolb200_options opt{};
+	lolb200_scene* scene = nullptr;
+	std::string source;
+	std::vector<char> image;
+	cudaLibrary_t lib = nullptr;
+	cudaKernel_t kernel = nullptr;
+	int sm_count = 0;
+	int blocks_per_sm = 1;
+	int regs = 0, smem = 0, local = 0, max_threads = 0;
+	lol_u32* counter = nullptr; /* device: [0] next chunk, [1] finished CTAs */
+	lol_u64* stats = nullptr;   /* device: 8 accumulators (options.counters) */
+	/* render_host staging */
+	lol_u32* frame = nullptr;
+	size_t frame_pixels = 0;
+	cudaStream_t stream = nullptr;
+	void* registered = nullptr; /* host surface pinned with cudaHostRegister */
+	size_t registered_bytes = 0;
+};
+
+/* ------------------------------------------------------------------ NVRTC -- */
+
+extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, void** image,
+                                     size_t* image_size, char** log) {
+	lolb200_options opt;
+	if (o)
+		opt = *o;
+	else
+		lolb200_options_default(&opt);
+	if (!src || !image || !image_size) {
+		lolb200_set_error("lolb200_compile_cubin: NULL argument");
+		return LOLB200_EINVAL;
+	}
+	*image = nullptr;
+	*image_size = 0;
+	if (log)
+		*log = nullptr;
+
+	nvrtcProgram prog;
+	nvrtcResult r = nvrtcCreateProgram(&prog, src, "lol_scene.cu", 0, nullptr, nullptr);
+	if (r != NVRTC_SUCCESS) {
+		lolb200_set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+		return LOLB200_ECOMPILE;
+	}
+	std::vector<const char*> args = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+	                                 "--extra-device-vectorization"};
+	if (opt.arith == LOLB200_ARITH_EXACT) {
+		/* One rounding per operation, IEEE div/sqrt, denormals kept: the
+		 * reference is SSE scalar code without FMA (reference Makefile:3). */
+		args.push_back("--fmad=false");
+		args.push_back("--prec-div=true");
+		args.push_back("--prec-sqrt=true");
+		args.push_back("--ftz=false");
+	} else {
+		args.push_back("--fmad=true");
+		args.push_back("--prec-div=false");
+		args.push_back("--prec-sqrt=false");
+		args.push_back("--ftz=true");
+	}
+	r = nvrtcCompileProgram(prog, (int)args.size(), args.data());
+	size_t log_size = 0;
+	nvrtcGetProgramLogSize(prog, &log_size);
+	std::string text(log_size ? log_size : 1, '\0');
+	if (log_size)
+		nvrtcGetProgramLog(prog, &text[0]);
+	if (log && log_size > 1) {
+		*log = (char*)malloc(log_size + 1);
+		memcpy(*log, text.c_str(), log_size);
+		(*log)[log_size] = 0;
+	}
+	if (r != NVRTC_SUCCESS) {
+		lolb200_set_error("NVRTC: %s\n%.3500s", nvrtcGetErrorString(r), text.c_str());
+		nvrtcDestroyProgram(&prog);
+		return LOLB200_ECOMPILE;
+	}
+	size_t n = 0;
+	r = nvrtcGetCUBINSize(prog, &n);
+	if (r != NVRTC_SUCCESS || n == 0) {
+		lolb200_set_error("nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+		nvrtcDestroyProgram(&prog);
+		return LOLB200_ECOMPILE;
+	}
+	*image = malloc(n);
+	nvrtcGetCUBIN(prog, (char*)*image);
+	*image_size = n;
+	nvrtcDestroyProgram(&prog);
+	return LOLB200_OK;
+}
+
+/* --------------------------------------------------------------- renderer -- */
+
+extern "C" int lolb200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" void lolb200_renderer_destroy(lolb200_renderer* r) {
+	if (!r)
+		return;
+	{
+		DeviceGuard g(r->device);
+		if (r->stream) {
+			cudaStreamSynchronize(r->stream);
+			cudaStreamDestroy(r->stream);
+		}
+		if (r->registered)
+			cudaHostUnregister(r->registered);
+		cudaFree(r->frame);
+		cudaFree(r->counter);
+		cudaFree(r->stats);
+		if (r->lib)
+			cudaLibraryUnload(r->lib);
+	}
+	lolb200_scene_free(r->scene);
+	delete r;
+}
+
+extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_options* o,
+                                       int device, lolb200_renderer** out) {
+	if (!s || !out) {
+		lolb200_set_error("lolb200_renderer_create: NULL argument");
+		return LOLB200_EINVAL;
+	}
+	*out = nullptr;
+	int rc = lolb200_scene_check(s);
+	if (rc != LOLB200_OK)
+		return rc;
+	int ndev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		lolb200_set_error("no CUDA device available (%s); liblolb200 has no CPU fallback",
+		                  ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+		return LOLB200_ENODEVICE;
+	}
+	if (device < 0 || device >= ndev) {
+		lolb200_set_error("device %d out of range (have %d)", device, ndev);
+		return LOLB200_EINVAL;
+	}
+
+	lolb200_renderer* r = new lolb200_renderer();
+	r->device = device;
+	if (o)
+		r->opt = *o;
+	else
+		lolb200_options_default(&r->opt);
+	r->scene = lolb200_scene_clone(s);
+
+	size_t len = 0;
+	char* src = lolb200_lower_cuda(s, &r->opt, &len);
+	if (!src) {
+		lolb200_renderer_destroy(r);
+		return LOLB200_EINVAL;
+	}
+	r->source.assign(src, len);
+	lolb200_free(src);
+
+	void* image = nullptr;
+	size_t image_size = 0;
+	rc = lolb200_compile_cubin(r->source.c_str(), &r->opt, &image, &image_size, nullptr);
+	if (rc != LOLB200_OK) {
+		lolb200_renderer_destroy(r);
+		return rc;
+	}
+	r->image.assign((char*)image, (char*)image + image_size);
+	free(image);
+
+#define CREATE_TRY(expr)                                                                 \
+	do {                                                                                 \
+		cudaError_t e_ = (expr);                                                         \
+		if (e_ != cudaSuccess) {                                                         \
+			lolb200_set_error("%s failed: %s", #expr, cudaGetErrorString(e_));           \
+			lolb200_renderer_destroy(r);                                                 \
+			return LOLB200_ECUDA;                                                        \
+		}                                                                                \
+	} while (0)
+
+	DeviceGuard g(device);
+	cudaDeviceProp prop;
+	CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) {
+		lolb200_set_error("device %d is sm_%d%d; this build targets sm_100a (B200) only", device,
+		                  prop.major, prop.minor);
+		lolb200_renderer_destroy(r);
+		return LOLB200_ENODEVICE;
+	}
+	r->sm_count = prop.multiProcessorCount;
+	CREATE_TRY(cudaLibraryLoadData(&r->lib, r->image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+	CREATE_TRY(cudaLibraryGetKernel(&r->kernel, r->lib, "lol_render"));
+	cudaFuncAttributes fa;
+	CREATE_TRY(cudaFuncGetAttributes(&fa, (const void*)r->kernel));
+	r->regs = fa.numRegs;
+	r->smem = (int)fa.sharedSizeBytes;
+	r->local = (int)fa.localSizeBytes;
+	r->max_threads = fa.maxThreadsPerBlock;
+	int occ = 0;
+	CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)r->kernel,
+	                                                         LOLB200_KERNEL_THREADS, 0));
+	r->blocks_per_sm = occ > 0 ? occ : 1;
+	CREATE_TRY(cudaMalloc(&r->counter, 2 * sizeof(lol_u32)));
+	CREATE_TRY(cudaMemset(r->counter, 0, 2 * sizeof(lol_u32)));
+	CREATE_TRY(cudaMalloc(&r->stats, 8 * sizeof(lol_u64)));
+	CREATE_TRY(cudaMemset(r->stats, 0, 8 * sizeof(lol_u64)));
+	CREATE_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+#undef CREATE_TRY
+	*out = r;
+	return LOLB200_OK;
+}
+
+extern "C" const char* lolb200_renderer_source(const lolb200_renderer* r) {
+	return r ? r->source.c_str() : nullptr;
+}
+
+extern "C" const void* lolb200_renderer_image(const lolb200_renderer* r, size_t* size) {
+	if (!r)
+		return nullptr;
+	if (size)
+		*size = r->image.size();
+	return r->image.data();
+}
+
+extern "C" int lolb200_renderer_kernel_info(const lolb200_renderer* r, int* regs, int* smem,
+                                            int* local, int* max_threads) {
+	if (!r)
+		return LOLB200_EINVAL;
+	if (regs) *regs = r->regs;
+	if (smem) *smem = r->smem;
+	if (local) *local = r->local;
+	if (max_threads) *max_threads = r->max_threads;
+	return LOLB200_OK;
+}
+
+extern "C" size_t lolb200_shard_pixels(int w, int h, int world, int band_rows) {
+	if (w <= 0 || h <= 0 || world <= 0)
+		return 0;
+	if (band_rows == 0)
+		band_rows = LOL_BAND_ROWS;
+	size_t bands = ((size_t)h + band_rows - 1) / band_rows;
+	size_t local = (bands + world - 1) / world;
+	return local * band_rows * (size_t)w;
+}
+
+/* Work chunks are chunk_w x 4 pixels.  Wide chunks mean fewer atomics on the
+ * one counter; narrow ones keep every warp busy when a shard is small. */
+static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands) {
+	const size_t warps = (size_t)r->sm_count * r->blocks_per_sm * (LOLB200_KERNEL_THREADS / 32);
+	for (lol_u32 cw = 64; cw > 8; cw >>= 1) {
+		size_t chunks = (((size_t)w + cw - 1) / cw) * local_bands;
+		if (chunks >= 16 * warps)
+			return cw;
+	}
+	return 8;
+}
+
+extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                                     const lolb200_pixfmt* fmt, const lolb200_shard* shard,
+                                     void* dst_dev, size_t pitch_px, const lolb200_aux* aux,
+                                     void* stream) {
+	if (!r || !dst_dev || w <= 0 || h <= 0 || pitch_px < (size_t)w) {
+		lolb200_set_error("lolb200_render_device: bad argument");
+		return LOLB200_EINVAL;
+	}
+	lolb200_shard sh = {0, 1, LOL_BAND_ROWS, 1};
+	if (shard)
+		sh = *shard;
+	if (sh.band_rows == 0)
+		sh.band_rows = LOL_BAND_ROWS;
+	if (sh.band_rows != LOL_BAND_ROWS || sh.world < 1 || sh.rank < 0 || sh.rank >= sh.world) {
+		lolb200_set_error("lolb200_render_device: bad shard (rank %d of %d, band_rows %d; "
+		                  "bands are %d rows)", sh.rank, sh.world, sh.band_rows, LOL_BAND_ROWS);
+		return LOLB200_EINVAL;
+	}
+	lolb200_pixfmt pf;
+	if (fmt)
+		pf = *fmt;
+	else
+		lolb200_pixfmt_default(&pf);
+
+	lolb200_camera c = cam ? *cam : r->scene->camera;
+	lolb200_camera_basis cb;
+	lolb200_camera_basis_compute(&c, w, h, &cb);
+
+	const size_t bands = ((size_t)h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
+	const size_t local_bands =
+		bands > (size_t)sh.rank ? (bands - sh.rank + sh.world - 1) / sh.world : 0;
+	if (local_bands == 0)
+		return LOLB200_OK;
+
+	lol_params P;
+	memset(&P, 0, sizeof P);
+	P.ox = cb.origin[0]; P.oy = cb.origin[1]; P.oz = cb.origin[2];
+	P.dx = cb.dir[0];    P.dy = cb.dir[1];    P.dz = cb.dir[2];
+	P.rx = cb.right[0];  P.ry = cb.right[1];  P.rz = cb.right[2];
+	P.ux = cb.up[0];     P.uy = cb.up[1];     P.uz = cb.up[2];
+	P.cw = cb.width;
+	P.ch = cb.height;
+	P.fw = (float)w;
+	P.fh = (float)h;
+	P.w = w;
+	P.h = h;
+	P.rank = sh.rank;
+	P.world = sh.world;
+	P.dst_full = sh.dst_full_frame ? 1 : 0;
+	P.pitch = (lol_u32)pitch_px;
+	P.chunk_w = pick_chunk_w(r, w, local_bands);
+	P.chunks_per_band = (lol_u32)(((size_t)w + P.chunk_w - 1) / P.chunk_w);
+	P.n_chunks = (lol_u32)(P.chunks_per_band * local_bands);
+	P.rshift = pf.rshift; P.gshift = pf.gshift; P.bshift = pf.bshift;
+	P.rloss = pf.rloss;   P.gloss = pf.gloss;   P.bloss = pf.bloss;
+	P.amask = pf.amask;
+	P.counter = r->counter;
+	P.dst = (lol_u32*)dst_dev;
+	if (aux) {
+		P.aux_dist = aux->dist;
+		P.aux_id = aux->id;
+		P.aux_primary = aux->primary_steps;
+		P.aux_shadow = aux->shadow_steps;
+	}
+	P.stats = r->stats;
+
+	DeviceGuard g(r->device);
+	const size_t warps_needed = P.n_chunks;
+	size_t grid = (size_t)r->sm_count * r->blocks_per_sm;
+	const size_t grid_needed = (warps_needed + LOLB200_KERNEL_THREADS / 32 - 1) /
+	                           (LOLB200_KERNEL_THREADS / 32);
+	if (grid > grid_needed)
+		grid = grid_needed;
+	void* args[] = {&P};
+	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3(LOLB200_KERNEL_THREADS),
+	                          args, 0, (cudaStream_t)stream));
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                                   const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes) {
+	if (!r || !pixels || w <= 0 || h <= 0 || pitch_bytes < (size_t)w * 4) {
+		lolb200_set_error("lolb200_render_host: bad argument");
+		return LOLB200_EINVAL;
+	}
+	DeviceGuard g(r->device);
+	const size_t need = (size_t)w * h;
+	if (r->frame_pixels < need) {
+		cudaFree(r->frame);
+		r->frame = nullptr;
+		r->frame_pixels = 0;
+		CUDA_TRY(cudaMalloc(&r->frame, need * sizeof(lol_u32)));
+		r->frame_pixels = need;
+	}
+	/* Pin the caller's surface once (SDL hands back the same pixels until the
+	 * window is resized) so the read-back is one DMA at PCIe speed. */
+	const size_t bytes = pitch_bytes * (size_t)h;
+	if (r->registered != pixels || r->registered_bytes != bytes) {
+		if (r->registered) {
+			cudaHostUnregister(r->registered);
+			r->registered = nullptr;
+		}
+		if (cudaHostRegister(pixels, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+			r->registered = pixels;
+			r->registered_bytes = bytes;
+		} else {
+			cudaGetLastError(); /* pageable copy still works, only slower */
+		}
+	}
+	int rc = lolb200_render_device(r, cam, w, h, fmt, nullptr, r->frame, (size_t)w, nullptr,
+	                               r->stream);
+	if (rc != LOLB200_OK)
+		return rc;
+	CUDA_TRY(cudaMemcpy2DAsync(pixels, pitch_bytes, r->frame, (size_t)w * 4, (size_t)w * 4, (size_t)h,
+	                           cudaMemcpyDeviceToHost, r->stream));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_read_counters(lolb200_renderer* r, uint64_t out[8]) {
+	if (!r || !out)
+		return LOLB200_EINVAL;
+	DeviceGuard g(r->device);
+	CUDA_TRY(cudaDeviceSynchronize());
+	CUDA_TRY(cudaMemcpy(out, r->stats, 8 * sizeof(lol_u64), cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemset(r->stats, 0, 8 * sizeof(lol_u64)));
+	return LOLB200_OK;
+}
+
+/* ------------------------------------------------------------ de-interleave -- */
+
+/* gathered: world compact shards back to back, each [local_band][4][w] padded
+ * to shard_pixels.  One thread moves four pixels of one row. */
+__global__ void __launch_bounds__(256)
+lol_deinterleave_kernel(const lol_u32* __restrict__ gathered, lol_u32* __restrict__ frame, int w,
+                        int h, int world, size_t shard_pixels, size_t pitch_px, int vec) {
+	const int quads = (w + 3) >> 2;
+	const size_t total = (size_t)quads * h;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+	     i += (size_t)gridDim.x * blockDim.x) {
+		const int y = (int)(i / quads);
+		const int x = (int)(i - (size_t)y * quads) << 2;
+		const int band = y / LOL_BAND_ROWS;
+		const int rank = band % world;
+		const size_t lrow = (size_t)(band / world) * LOL_BAND_ROWS + (y % LOL_BAND_ROWS);
+		const lol_u32* src = gathered + rank * shard_pixels + lrow * w + x;
+		lol_u32* dst = frame + (size_t)y * pitch_px + x;
+		if (vec && x + 4 <= w) {
+			*reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+		} else {
+			for (int k = 0; k < 4 && x + k < w; ++k)
+				dst[k] = src[k];
+		}
+	}
+}
+
+extern "C" int lolb200_deinterleave_device(const void* gathered, void* frame, int w, int h,
+                                           int world, int band_rows, size_t shard_pixels,
+                                           size_t pitch_px, void* stream) {
+	if (!gathered || !frame || w <= 0 || h <= 0 || world < 1 ||
+	    (band_rows != 0 && band_rows != LOL_BAND_ROWS) || pitch_px < (size_t)w) {
+		lolb200_set_error("lolb200_deinterleave_device: bad argument");
+		return LOLB200_EINVAL;
+	}
+	const int vec = (w % 4 == 0) && (pitch_px % 4 == 0) && (shard_pixels % 4 == 0) &&
+	                ((uintptr_t)gathered % 16 == 0) && ((uintptr_t)frame % 16 == 0);
+	const size_t total = (size_t)((w + 3) / 4) * h;
+	int sm = 148;
+	int dev = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess)
+		cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+	size_t blocks = (total + 255) / 256;
+	if (blocks > (size_t)sm * 8)
+		blocks = (size_t)sm * 8;
+	lol_deinterleave_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+		(const lol_u32*)gathered, (lol_u32*)frame, w, h, world, shard_pixels, pitch_px, vec);
+	CUDA_TRY(cudaGetLastError());
+	return LOLB200_OK;
+}
+
+/* ---------------------------------------------------------------- CUDA IPC -- */
+
+extern "C" int lolb200_ipc_export(void* dev_ptr, uint8_t handle[64]) {
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+	memcpy(handle, &h, 64);
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_ipc_open(const uint8_t handle[64], void** dev_ptr) {
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_ipc_close(void* dev_ptr) {
+	CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+	return LOLB200_OK;
+}
+
+/* --------------------------------------------------- FP32 peak microbenchmark -- */
+
+/* 8 independent FFMA chains per thread, register operands only. */
+__global__ void __launch_bounds__(256) lol_ffma_peak_kernel(float* out, int iters, float a, float b) {
+	float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+	float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+			x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+		}
+	}
+	float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+	if (s == 123.456f)
+		out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" double lolb200_measure_fp32_peak(int device, int iters, double* ms_out) {
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+		cudaGetLastError();
+		lolb200_set_error("lolb200_measure_fp32_peak: no such device");
+		return -1.0;
+	}
+	DeviceGuard g(device);
+	int sm = 0;
+	cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+	if (iters <= 0)
+		iters = 4096;
+	const int blocks = sm * 8, threads = 256;
+	float* out = nullptr;
+	if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) {
+		lolb200_set_error("lolb200_measure_fp32_peak: cudaMalloc failed");
+		return -1.0;
+	}
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	float best = 1e30f;
+	for (int rep = 0; rep < 6; ++rep) { /* first reps warm up clocks and I-cache */
+		cudaEventRecord(e0);
+		lol_ffma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (rep >= 2 && ms < best)
+			best = ms;
+	}
+	cudaError_t e = cudaGetLastError();
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(out);
+	if (e != cudaSuccess) {
+		lolb200_set_error("lolb200_measure_fp32_peak: %s", cudaGetErrorString(e));
+		return -1.0;
+	}
+	if (ms_out)
+		*ms_out = best;
+	const double flop = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
+	return flop / (best * 1e-3) / 1e12;
+}

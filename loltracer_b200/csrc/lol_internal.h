@@ -10,6 +10,12 @@ extern "C" {
 
 void lolb200_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
 int lolb200_scene_check(const lolb200_scene* s);
+/* Scene-dependent licences for the exact work-skipping shortcuts (lol_lower.c). */
+int lolb200_can_skip_black_miss(const lolb200_scene* s);
+int lolb200_can_cull_backfacing(const lolb200_scene* s);
+
+/* Threads per CTA of the generated kernel (8 warps). */
+#define LOLB200_KERNEL_THREADS 256
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,427 @@
+/*
+ * lol_lower.c -- lowers a scene to specialised CUDA C: the code generator.
+ *
+ * GPU analogue of generate_sdf() / generate_obj_dist()
+ * (tracing_jit_renderer.dasc:76-216): the SDF tree becomes straight-line code
+ * with every constant baked in as an immediate, and the scene-independent
+ * pipeline text (lol_kernel.cuh) is spliced around it.  Long runs of top-level
+ * objects of one shape (the 1024-primitive synthetic scene) become a loop over a
+ * __constant__ parameter table instead of 25k unrolled instructions per call
+ * site.  Pure host C: testable without a device.
+ */
+#include "lol_internal.h"
+#include "lolb200.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+extern const char lol_kernel_text[]; /* lol_kernel.cuh, embedded by lol_kernel_text.c */
+extern const char lol_params_text[]; /* lol_params.h, likewise */
+
+/* ------------------------------------------------------------ string builder */
+
+struct sb {
+	char* p;
+	size_t len, cap;
+};
+
+static void sb_reserve(struct sb* b, size_t more) {
+	if (b->len + more + 1 > b->cap) {
+		while (b->len + more + 1 > b->cap)
+			b->cap = b->cap ? b->cap * 2 : 1 << 14;
+		b->p = realloc(b->p, b->cap);
+	}
+}
+
+static void sb_putn(struct sb* b, const char* s, size_t n) {
+	sb_reserve(b, n);
+	memcpy(b->p + b->len, s, n);
+	b->len += n;
+	b->p[b->len] = 0;
+}
+
+static void sb_printf(struct sb* b, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+static void sb_printf(struct sb* b, const char* fmt, ...) {
+	va_list ap;
+	char tmp[512];
+	int n;
+	va_start(ap, fmt);
+	n = vsnprintf(tmp, sizeof tmp, fmt, ap);
+	va_end(ap);
+	if (n < 0)
+		return;
+	if ((size_t)n < sizeof tmp) {
+		sb_putn(b, tmp, (size_t)n);
+		return;
+	}
+	sb_reserve(b, (size_t)n);
+	va_start(ap, fmt);
+	vsnprintf(b->p + b->len, (size_t)n + 1, fmt, ap);
+	va_end(ap);
+	b->len += (size_t)n;
+}
+
+static uint32_t f2u(float f) {
+	uint32_t u;
+	memcpy(&u, &f, 4);
+	return u;
+}
+
+/* A float as the kernel sees it: exact bits, with the decimal value as a comment. */
+static void sb_float(struct sb* b, float f) {
+	sb_printf(b, "LOL_F(0x%08x /*%.9g*/)", f2u(f), (double)f);
+}
+
+/* The same inside a table initialiser: tables hold raw bits (static
+ * initialisers cannot call __int_as_float) and are read through LOL_TF(). */
+static void sb_bits(struct sb* b, float f) {
+	sb_printf(b, "0x%08xu /*%.9g*/", f2u(f), (double)f);
+}
+
+/* ------------------------------------------------------------ distance code */
+
+/* Where a constant comes from: an immediate, or slot j of the current row of a
+ * run table (loop mode). */
+struct cgen {
+	const lolb200_scene* s;
+	struct sb* out;
+	int tmp;      /* next temporary number                      */
+	int in_loop;  /* 1: constants are c[j], gathered into row[] */
+	float* row;
+	size_t nrow, caprow;
+	const char* indent;
+};
+
+static void cst(struct cgen* g, float v) {
+	if (!g->in_loop) {
+		sb_float(g->out, v);
+		return;
+	}
+	if (g->nrow == g->caprow) {
+		g->caprow = g->caprow ? g->caprow * 2 : 16;
+		g->row = realloc(g->row, g->caprow * sizeof(float));
+	}
+	sb_printf(g->out, "LOL_TF(c[%zu])", g->nrow);
+	g->row[g->nrow++] = v;
+}
+
+static int is_pos_zero(float v) { return f2u(v) == 0u; }
+
+/* `x - c`; x - (+0) is x for every x, so it is dropped outside loops. */
+static void coord_minus(struct cgen* g, const char* x, float c) {
+	if (!g->in_loop && is_pos_zero(c)) {
+		sb_printf(g->out, "%s", x);
+		return;
+	}
+	sb_printf(g->out, "%s - ", x);
+	cst(g, c);
+}
+
+/* get_obj_dist (naive_renderer.c:10-28), one object -> `const float tN = ...;`.
+ * Returns N.  Children of a smooth union see the same (x, y, z). */
+static int emit_node(struct cgen* g, uint32_t idx) {
+	const lolb200_object* o = &g->s->nodes[idx];
+	int me;
+
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: /* sdSphere, sdf.h:8-10 */
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst float t%d = lol_len(", g->indent, me);
+		coord_minus(g, "x", o->point[0]);
+		sb_printf(g->out, ", ");
+		coord_minus(g, "y", o->point[1]);
+		sb_printf(g->out, ", ");
+		coord_minus(g, "z", o->point[2]);
+		sb_printf(g->out, ") - ");
+		cst(g, o->radius);
+		sb_printf(g->out, ";\n");
+		return me;
+	case LOLB200_OBJ_BOX: /* sdRoundBox, sdf.h:18-22 */
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst float t%d = lol_roundbox(fabsf(", g->indent, me);
+		coord_minus(g, "x", o->point[0]);
+		sb_printf(g->out, ") - ");
+		cst(g, o->point2[0]);
+		sb_printf(g->out, ", fabsf(");
+		coord_minus(g, "y", o->point[1]);
+		sb_printf(g->out, ") - ");
+		cst(g, o->point2[1]);
+		sb_printf(g->out, ", fabsf(");
+		coord_minus(g, "z", o->point[2]);
+		sb_printf(g->out, ") - ");
+		cst(g, o->point2[2]);
+		sb_printf(g->out, ", ");
+		cst(g, o->radius);
+		sb_printf(g->out, ");\n");
+		return me;
+	case LOLB200_OBJ_PLANE: /* point.y, naive_renderer.c:19-20 */
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst float t%d = ", g->indent, me);
+		coord_minus(g, "y", o->point[1]);
+		sb_printf(g->out, ";\n");
+		return me;
+	default: { /* sminf(a, b, k), naive_renderer.c:21-24 */
+		int a = emit_node(g, (uint32_t)o->a);
+		int b = emit_node(g, (uint32_t)o->b);
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst float t%d = lol_smin(t%d, t%d, ", g->indent, me, a, b);
+		cst(g, o->smoothness);
+		sb_printf(g->out, ");\n");
+		return me;
+	}
+	}
+}
+
+/* Shape of a subtree without its constants: objects with equal signatures run
+ * the same instructions on different table rows. */
+static void signature(const lolb200_scene* s, uint32_t idx, struct sb* out) {
+	const lolb200_object* o = &s->nodes[idx];
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: sb_putn(out, "S", 1); break;
+	case LOLB200_OBJ_BOX: sb_putn(out, "B", 1); break;
+	case LOLB200_OBJ_PLANE: sb_putn(out, "P", 1); break;
+	default:
+		sb_putn(out, "U(", 2);
+		signature(s, (uint32_t)o->a, out);
+		sb_putn(out, ",", 1);
+		signature(s, (uint32_t)o->b, out);
+		sb_putn(out, ")", 1);
+	}
+}
+
+static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold) {
+	struct sb body = {0}, tables = {0};
+	struct cgen g = {.s = s, .out = &body};
+	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
+	size_t table_bytes = 0;
+	int run_no = 0;
+
+	for (uint32_t i = 0; i < s->n_objects; i++) {
+		struct sb sig = {0};
+		signature(s, s->objects[i], &sig);
+		sigs[i] = sig.p;
+	}
+
+	sb_printf(&body,
+	          "// sdf (naive_renderer.c:30-44): running strict-< minimum over the top-level\n"
+	          "// objects, ids 1..n in file order, (INF, 0) when nothing is closer.\n"
+	          "__device__ __forceinline__ float lol_sdf(const float x, const float y, const float z,\n"
+	          "                                         lol_u32& id) {\n"
+	          "\tfloat best = LOL_INF;\n"
+	          "\tlol_u32 bid = 0u;\n");
+
+	for (uint32_t i = 0; i < s->n_objects;) {
+		uint32_t j = i + 1;
+		while (j < s->n_objects && strcmp(sigs[j], sigs[i]) == 0)
+			j++;
+		if ((int)(j - i) >= loop_threshold) {
+			/* objects i .. j-1 share one shape: loop over a parameter table */
+			size_t per_row = 0;
+			sb_printf(&body, "\t// objects %u..%u: %u x %s\n", i + 1, j, j - i, sigs[i]);
+			sb_printf(&tables, "LOL_TABLE_SPACE lol_u32 lol_run%d[] = {\n", run_no);
+			for (uint32_t k = i; k < j; k++) {
+				struct sb scratch = {0};
+				struct cgen r = {.s = s, .out = (k == i) ? &body : &scratch, .in_loop = 1,
+				                 .indent = "\t\t"};
+				if (k == i) {
+					sb_printf(&body, "#pragma unroll 2\n\tfor (int i = 0; i < %u; ++i) {\n",
+					          j - i);
+					sb_printf(&body, "\t\tconst lol_u32* c = lol_run%d + i * LOL_RUN%d_STRIDE;\n",
+					          run_no, run_no);
+				}
+				int t = emit_node(&r, s->objects[k]);
+				if (k == i) {
+					sb_printf(&body,
+					          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu + "
+					          "(lol_u32)i;\n\t\t}\n\t}\n",
+					          t, t, i + 1);
+					per_row = r.nrow;
+				}
+				sb_printf(&tables, "\t");
+				for (size_t q = 0; q < r.nrow; q++) {
+					sb_bits(&tables, r.row[q]);
+					sb_printf(&tables, ", ");
+				}
+				sb_printf(&tables, "\n");
+				free(r.row);
+				free(scratch.p);
+			}
+			sb_printf(&tables, "};\n#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
+			table_bytes += per_row * (j - i) * sizeof(float);
+			run_no++;
+		} else {
+			for (uint32_t k = i; k < j; k++) {
+				g.indent = "\t\t";
+				sb_printf(&body, "\t{ // object %u: %s\n", k + 1, sigs[k]);
+				g.tmp = 0;
+				int t = emit_node(&g, s->objects[k]);
+				sb_printf(&body,
+				          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu;\n\t\t}\n\t}\n",
+				          t, t, k + 1);
+			}
+		}
+		i = j;
+	}
+	sb_printf(&body, "\tid = bid;\n\treturn best;\n}\n");
+
+	/* 64 KB of __constant__ space; keep a margin for the kernel parameters. */
+	sb_printf(out, "#define LOL_TABLE_SPACE %s\n",
+	          table_bytes <= 56 * 1024 ? "__constant__" : "__device__ const");
+	if (tables.p)
+		sb_putn(out, tables.p, tables.len);
+	sb_putn(out, body.p, body.len);
+
+	for (uint32_t i = 0; i < s->n_objects; i++)
+		free(sigs[i]);
+	free(sigs);
+	free(body.p);
+	free(tables.p);
+}
+
+/* ----------------------------------------------------- exact-skip conditions */
+
+static int finite3(const float v[3]) { return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]); }
+static int zero3(const float v[3]) { return v[0] == 0.f && v[1] == 0.f && v[2] == 0.f; }
+
+/* All light intensities and the ambient colour finite: `finite * 0 == 0` holds. */
+static int lights_finite(const lolb200_scene* s) {
+	for (uint32_t i = 0; i < s->n_lights; i++)
+		if (!finite3(s->lights[i].diffuse_intensity) || !finite3(s->lights[i].specular_intensity))
+			return 0;
+	return finite3(s->ambient_color);
+}
+
+/* powf(x in [0,1], shininess) stays finite iff shininess >= 0 (powf(0,0) = 1). */
+static int shininess_ok(const lolb200_material* m) {
+	return isfinite(m->shininess) && m->shininess >= 0.f;
+}
+
+/* Miss pixels take material 0 (naive_renderer.c:105-109).  With kd = ks = ka = 0
+ * and everything else finite each term of get_light is +-0 and the pixel is
+ * exactly black. */
+int lolb200_can_skip_black_miss(const lolb200_scene* s) {
+	const lolb200_material* m = &s->materials[0];
+	return lights_finite(s) && shininess_ok(m) && zero3(m->diffuse) && zero3(m->specular) &&
+	       zero3(m->ambient);
+}
+
+/* A light with clamp(n.l) == 0 adds (I*(shadow*0))*k = +-0 twice: exact for
+ * finite I, k and finite powf, i.e. for every material a hit can select. */
+int lolb200_can_cull_backfacing(const lolb200_scene* s) {
+	if (!lights_finite(s))
+		return 0;
+	for (uint32_t i = 0; i < s->n_materials; i++) {
+		const lolb200_material* m = &s->materials[i];
+		if (!shininess_ok(m) || !finite3(m->diffuse) || !finite3(m->specular))
+			return 0;
+	}
+	return 1;
+}
+
+/* ------------------------------------------------------------------- driver */
+
+static void emit_tables(struct sb* out, const lolb200_scene* s) {
+	sb_printf(out, "#define LOL_NLIGHTS %u\n#define LOL_NOBJECTS %u\n", s->n_lights, s->n_objects);
+	sb_printf(out, "#define LOL_AMBIENT_R ");
+	sb_float(out, s->ambient_color[0]);
+	sb_printf(out, "\n#define LOL_AMBIENT_G ");
+	sb_float(out, s->ambient_color[1]);
+	sb_printf(out, "\n#define LOL_AMBIENT_B ");
+	sb_float(out, s->ambient_color[2]);
+	sb_printf(out, "\n");
+
+	/* get_material (naive_renderer.c:102-112) resolved per object id at lowering
+	 * time: row 0 = material 0 (misses), row i = material of top-level object i.
+	 * Row: shininess, diffuse[3], specular[3], ambient[3], 2 pad. */
+	sb_printf(out, "__device__ const lol_u32 lol_materials[] = {\n");
+	for (uint32_t id = 0; id <= s->n_objects; id++) {
+		uint32_t mi = id ? s->nodes[s->objects[id - 1]].material : 0;
+		const lolb200_material* m = &s->materials[mi];
+		const float row[10] = {m->shininess,   m->diffuse[0],  m->diffuse[1], m->diffuse[2],
+		                       m->specular[0], m->specular[1], m->specular[2], m->ambient[0],
+		                       m->ambient[1],  m->ambient[2]};
+		sb_printf(out, "\t/* id %u -> material #%u */ ", id, mi);
+		for (int k = 0; k < 10; k++) {
+			sb_bits(out, row[k]);
+			sb_printf(out, ", ");
+		}
+		sb_printf(out, "0u, 0u,\n");
+	}
+	sb_printf(out, "};\n");
+
+	sb_printf(out,
+	          "// struct light (scene.h:52-56) by index; `i` is a compile-time constant at\n"
+	          "// every call site, so the switch folds to immediates.\n"
+	          "__device__ __forceinline__ void lol_light(const int i, float& px, float& py, "
+	          "float& pz,\n\t\tfloat& dr, float& dg, float& db, float& sr, float& sg, float& sb) "
+	          "{\n\tswitch (i) {\n");
+	for (uint32_t i = 0; i < s->n_lights; i++) {
+		const lolb200_light* l = &s->lights[i];
+		const float v[9] = {l->point[0], l->point[1], l->point[2],
+		                    l->diffuse_intensity[0], l->diffuse_intensity[1], l->diffuse_intensity[2],
+		                    l->specular_intensity[0], l->specular_intensity[1], l->specular_intensity[2]};
+		static const char* names[9] = {"px", "py", "pz", "dr", "dg", "db", "sr", "sg", "sb"};
+		sb_printf(out, "\t%s %u:\n", i + 1 == s->n_lights ? "default: // light" : "case", i);
+		for (int k = 0; k < 9; k++) {
+			sb_printf(out, "\t\t%s = ", names[k]);
+			sb_float(out, v[k]);
+			sb_printf(out, ";\n");
+		}
+		sb_printf(out, "\t\tbreak;\n");
+	}
+	if (s->n_lights == 0)
+		sb_printf(out, "\tdefault: px = py = pz = dr = dg = db = sr = sg = sb = 0.f;\n");
+	sb_printf(out, "\t}\n}\n");
+}
+
+char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, size_t* len) {
+	lolb200_options o;
+	struct sb out = {0};
+	const char* marker;
+	int variant, threshold;
+
+	if (lolb200_scene_check(s) != LOLB200_OK)
+		return NULL;
+	if (opt)
+		o = *opt;
+	else
+		lolb200_options_default(&o);
+	variant = o.variant ? o.variant : 1;
+	threshold = o.loop_threshold > 0 ? o.loop_threshold : 16;
+	if (variant != 1 && variant != 2) {
+		lolb200_set_error("unknown kernel variant %d", variant);
+		return NULL;
+	}
+
+	sb_printf(&out, "// Generated by lolb200_lower_cuda (ABI %d) -- do not edit.\n",
+	          LOLB200_ABI_VERSION);
+	sb_printf(&out, "// scene: %u objects (%u nodes), %u lights, %u materials, %llu FLOP per sdf()\n",
+	          s->n_objects, s->n_nodes, s->n_lights, s->n_materials,
+	          (unsigned long long)lolb200_scene_flops_per_eval(s));
+	sb_printf(&out, "#define LOL_EXACT %d\n", o.arith == LOLB200_ARITH_EXACT);
+	sb_printf(&out, "#define LOL_SKIP_MISS %d\n", o.skip_black_miss && lolb200_can_skip_black_miss(s));
+	sb_printf(&out, "#define LOL_CULL %d\n", o.cull_backfacing && lolb200_can_cull_backfacing(s));
+	sb_printf(&out, "#define LOL_SHADOW_EARLY %d\n", o.shadow_early_out != 0);
+	sb_printf(&out, "#define LOL_COUNTERS %d\n", o.counters != 0);
+	sb_printf(&out, "#define LOL_VARIANT %d\n", variant);
+	sb_printf(&out, "#define LOL_THREADS %d\n", LOLB200_KERNEL_THREADS);
+
+	marker = strstr(lol_kernel_text, "//@@SCENE@@");
+	if (!marker) {
+		lolb200_set_error("kernel text has no scene marker");
+		free(out.p);
+		return NULL;
+	}
+	sb_putn(&out, lol_params_text, strlen(lol_params_text));
+	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
+	emit_tables(&out, s);
+	emit_sdf(&out, s, threshold);
+	sb_putn(&out, marker, strlen(marker));
+
+	if (len)
+		*len = out.len;
+	return out.p;
+}

@@ -1,0 +1,176 @@
+"""ctypes views of the CPU checkers (TEST INFRASTRUCTURE).
+
+  liblol_oracle.so        oracle/lol_oracle.c, our restatement ("port")
+  _ref/liblolref.so       the reference's own naive_renderer.c ("reference");
+                          present when it was built in the container that has
+                          /root/reference and travelled with the snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PORT_PATH = os.path.join(ROOT, "oracle", "liblol_oracle.so")
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "liblolref.so")
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        L = C.CDLL(PORT_PATH)
+        L.lolo_render.restype = C.c_double
+        L.lolo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p] * 6
+        L.lolo_sdf.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3),
+                               C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+        _port = L
+    return _port
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_PATH)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_PATH)
+        L.lolref_scene_load.restype = C.c_void_p
+        L.lolref_scene_load.argtypes = [C.c_char_p]
+        L.lolref_scene_load_string.restype = C.c_void_p
+        L.lolref_scene_load_string.argtypes = [C.c_char_p, C.c_size_t]
+        L.lolref_scene_free.argtypes = [C.c_void_p]
+        L.lolref_scene_set_camera.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3),
+                                              C.POINTER(C.c_float * 3)]
+        L.lolref_scene_flatten.restype = C.c_void_p
+        L.lolref_scene_flatten.argtypes = [C.c_void_p]
+        L.lolref_render_protocol.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p]
+        L.lolref_probe.restype = C.c_double
+        L.lolref_probe.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] * 3
+        L.lolref_sdf.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_uint32)]
+        _ref = L
+    return _ref
+
+
+def nthreads() -> int:
+    return max(1, len(os.sched_getaffinity(0)))
+
+
+def _rows(h, y0, y1, ystride):
+    y1 = h if y1 is None else y1
+    return y1, (y1 - y0 + ystride - 1) // ystride
+
+
+def port_render(scene, w, h, camera=None, mode=0, y0=0, y1=None, ystride=1, threads=None,
+                counts=False):
+    """scene: loltracer_b200.Scene.  Returns dict(dist, id, rgba[, nprimary, nshadow], ms, totals)."""
+    y1, rows = _rows(h, y0, y1, ystride)
+    dist = np.zeros((rows, w), np.float32)
+    ids = np.zeros((rows, w), np.uint32)
+    rgba = np.zeros((rows, w), np.uint32)
+    npr = np.zeros((rows, w), np.uint16) if counts else None
+    nsh = np.zeros((rows, w), np.uint16) if counts else None
+    tot = (C.c_uint64 * 4)()
+    ms = port().lolo_render(
+        C.cast(scene._ptr, C.c_void_p), C.cast(C.byref(camera), C.c_void_p) if camera else None,
+        mode, w, h, y0, y1, ystride, threads or nthreads(), dist.ctypes.data, ids.ctypes.data,
+        rgba.ctypes.data, npr.ctypes.data if counts else None, nsh.ctypes.data if counts else None,
+        C.cast(tot, C.c_void_p))
+    out = dict(dist=dist, id=ids, rgba=rgba, ms=ms,
+               totals=dict(primary=int(tot[0]), normal=int(tot[1]), shadow=int(tot[2]), hits=int(tot[3])))
+    if counts:
+        out.update(nprimary=npr, nshadow=nsh)
+    return out
+
+
+class RefScene:
+    """A scene held by the compiled reference (struct scene*, built by its own scene.c)."""
+
+    def __init__(self, path=None, text=None):
+        if path is not None:
+            self.ptr = ref().lolref_scene_load(os.fsencode(path))
+        else:
+            raw = text.encode()
+            self.ptr = ref().lolref_scene_load_string(raw, len(raw))
+        if not self.ptr:
+            raise RuntimeError("reference failed to load the scene")
+
+    def set_camera(self, point, direction):
+        p = (C.c_float * 3)(*point)
+        d = (C.c_float * 3)(*direction)
+        ref().lolref_scene_set_camera(self.ptr, C.byref(p), C.byref(d))
+
+    def flatten(self):
+        """The reference's structs through the backend's translation -> SceneStruct pointer."""
+        from loltracer_b200.api import SceneStruct, Scene
+
+        p = ref().lolref_scene_flatten(self.ptr)
+        return Scene(C.cast(p, C.POINTER(SceneStruct)))
+
+    def probe(self, w, h, y0=0, y1=None, ystride=1, threads=None):
+        y1, rows = _rows(h, y0, y1, ystride)
+        dist = np.zeros((rows, w), np.float32)
+        ids = np.zeros((rows, w), np.uint32)
+        rgba = np.zeros((rows, w), np.uint32)
+        ms = ref().lolref_probe(self.ptr, w, h, y0, y1, ystride, threads or nthreads(),
+                                dist.ctypes.data, ids.ctypes.data, rgba.ctypes.data)
+        return dict(dist=dist, id=ids, rgba=rgba, ms=ms)
+
+    def render_protocol(self, w, h, threads=None, frames=1):
+        """Through the unmodified render_thread() and main.c's semaphore protocol."""
+        px = np.zeros((h, w), np.uint32)
+        ms = (C.c_double * frames)()
+        ref().lolref_render_protocol(self.ptr, w, h, threads or nthreads(), frames,
+                                     px.ctypes.data, C.cast(ms, C.c_void_p))
+        return px, list(ms)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _ref is not None:
+            _ref.lolref_scene_free(self.ptr)
+            self.ptr = None
+
+
+def frame_hash(px: np.ndarray) -> str:
+    """h = h*1000003 + pixel over row-major pixels, 64-bit wrap."""
+    v = np.ascontiguousarray(px, dtype=np.uint32).ravel().astype(np.uint64)
+    n = v.size
+    mult = np.uint64(1000003)
+    # Horner in blocks: h = sum v[i] * m^(n-1-i)  (mod 2^64)
+    with np.errstate(over="ignore"):
+        pw = np.empty(n, np.uint64)
+        # powers by repeated doubling
+        pw[0] = 1
+        filled = 1
+        while filled < n:
+            step = min(filled, n - filled)
+            pw[filled:filled + step] = pw[:step] * (pw[filled - 1] * mult)
+            filled += step
+        h = np.sum(v * pw[::-1], dtype=np.uint64)
+    return f"{int(h):016x}"
+
+
+def compare_frames(got_rgba, got_id, want_rgba, want_id):
+    """North-star tolerances: hit/miss mask agreement and per-channel RGB error on
+    agreeing hits.  Returns dict(mask_agree, max_rgb_err, n_rgb_off, n_mask_off)."""
+    got_hit = got_id != 0
+    want_hit = want_id != 0
+    agree = got_hit == want_hit
+    both = got_hit & want_hit
+    def ch(a, s):
+        return ((a >> s) & 0xFF).astype(np.int32)
+    err = np.zeros(got_rgba.shape, np.int32)
+    for s in (16, 8, 0):
+        err = np.maximum(err, np.abs(ch(got_rgba, s) - ch(want_rgba, s)))
+    max_err = int(err[both].max()) if both.any() else 0
+    miss_both = (~got_hit) & (~want_hit)
+    miss_err = int(err[miss_both].max()) if miss_both.any() else 0
+    return dict(mask_agree=float(agree.mean()), n_mask_off=int((~agree).sum()),
+                max_rgb_err=max_err, n_rgb_off=int((err[both] > 0).sum()),
+                max_miss_rgb_err=miss_err, id_agree=float((got_id == want_id).mean()))
