@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s and ms/frame of the sphere-tracing hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scene scene4] [--size 3840x2160]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      the reference's CPU renderer, host cores
+
+A step is one frame of the workload (default: scene4.lol at 3840x2160, BASELINE
+config C3).  With N > 1 the frame is sharded in 4-row bands, band b -> rank b % N;
+every step ends with the complete frame on rank 0 (NCCL gather + de-interleave,
+or --gather peer: ranks store straight into rank 0's frame over NVLink).
+
+Prints ONE JSON line (rank 0).  `value` is whole-job Mrays/s with the frame left
+in HBM; `e2e` is the same metric through the host-surface entry point
+(lolb200_render_host: camera in, pixels copied into a host buffer).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "Mrays/s"
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45, SURVEY.md 8d
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default="scene4")
+    ap.add_argument("--size", default="3840x2160")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-scenes", action="store_true",
+                    help="also time the other example scenes (extra keys, same JSON line)")
+    return ap.parse_args()
+
+
+def load_scene(lb, name):
+    if name == "synthetic":
+        from loltracer_b200 import scenegen
+        return lb.Scene.from_string(scenegen.synthetic_scene_text())
+    path = name if os.path.exists(name) else os.path.join(ROOT, "tests", "golden", "scenes", name + ".lol")
+    return lb.Scene.from_file(path)
+
+
+# ------------------------------------------------------------------ clocks --
+
+REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+           0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and clock-event reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------ CPU baseline --
+
+
+def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False):
+    """The reference's naive renderer (oracle/_ref, built from its own sources) -- or the
+    oracle port when that library did not travel -- on every `ystride`-th scanline of the
+    w x h frame, all host threads.  Returns (best_ms, rays, kind, cores, totals)."""
+    import oracle_lib as ol
+    import loltracer_b200 as lb
+
+    cores = ol.nthreads()
+    rows = (h + ystride - 1) // ystride
+    rays = rows * w
+    scene = load_scene(lb, scene_name)
+    totals = ol.port_render(scene, w, h, ystride=ystride)["totals"]  # also warms the threads up
+    best = None
+    if ol.have_ref() and not force_port and scene_name != "synthetic-port":
+        kind = "reference"
+        if scene_name == "synthetic":
+            from loltracer_b200 import scenegen
+            rs = ol.RefScene(text=scenegen.synthetic_scene_text())
+        else:
+            path = scene_name if os.path.exists(scene_name) else os.path.join(
+                ROOT, "tests", "golden", "scenes", scene_name + ".lol")
+            rs = ol.RefScene(path=path)
+        for _ in range(repeats):
+            ms = rs.probe(w, h, ystride=ystride)["ms"]
+            best = ms if best is None else min(best, ms)
+    else:
+        kind = "port"
+        for _ in range(repeats):
+            ms = ol.port_render(scene, w, h, ystride=ystride)["ms"]
+            best = ms if best is None else min(best, ms)
+    return best, rays, kind, cores, totals
+
+
+def run_reference(args, w, h):
+    """--impl reference: the reference's CPU implementation of the path, host cores only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as entry
+    entry.build()
+    # size the sample so that (steps + warmup) samples end within ~2 minutes
+    probe_stride = 64
+    ms, rays, kind, cores, _ = cpu_sample(args.scene, w, h, probe_stride)
+    per_row_ms = ms / ((h + probe_stride - 1) // probe_stride)
+    budget_ms = 100e3 / max(1, args.steps + args.warmup)
+    stride = 1
+    while stride < 64 and per_row_ms * ((h + stride - 1) // stride) > budget_ms:
+        stride *= 2
+    for _ in range(args.warmup):
+        cpu_sample(args.scene, w, h, stride)
+    t_total, rays = 0.0, 0
+    for _ in range(args.steps):
+        ms, rays, kind, cores, _ = cpu_sample(args.scene, w, h, stride)
+        t_total += ms
+    ms_per_step = t_total / args.steps
+    value = rays / (ms_per_step * 1e-3) / 1e6
+    sample = (f"every {stride}th scanline of the {w}x{h} frame ({rays} primary rays per step), "
+              f"{'naive_renderer.c compiled unmodified' if kind == 'reference' else 'oracle port'}, "
+              f"{cores} threads pulling scanlines from one atomic counter")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "ms_per_frame_extrapolated": ms_per_step * (w * h / rays),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{args.scene}.lol at {w}x{h}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+# --------------------------------------------------------------- FLOP model --
+
+
+def flops_model(f_sdf, n_lights, pixels, primary, normal, shadow, shaded, rays_marched, rays_culled):
+    """SURVEY.md 8d convention: F = E*F_sdf + 9*n_primary + 12*n_shadow + 56 (normal
+    assembly, per shaded pixel) + 95 per light shaded (+20 for a culled one: L-p,
+    normalise, n.l) + 50 per pixel (camera ray, ambient, clamp, gamma, pack)."""
+    return (f_sdf * (primary + normal + shadow) + 9 * primary + 12 * shadow + 56 * shaded +
+            95 * rays_marched + 20 * rays_culled + 50 * pixels)
+
+
+# ------------------------------------------------------------------- main --
+
+
+def main():
+    args = parse_args()
+    w, h = (int(x) for x in args.size.lower().split("x"))
+    if args.impl == "reference":
+        return run_reference(args, w, h)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    import loltracer_b200 as lb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus) and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: liblolb200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+
+    scene = load_scene(lb, args.scene)
+    opt = lb.Options.default(variant=args.variant, arith=1 if args.arith == "fast" else 0)
+    renderer = lb.Renderer(scene, opt, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    K, W = args.steps, args.warmup
+
+    shard_px = lb.shard_pixels(w, h, world)
+    frame = torch.zeros((h, w), dtype=torch.int32, device=dev) if rank == 0 else None
+    if world > 1:
+        shard = lb.Shard(rank=rank, world=world, band_rows=0, dst_full_frame=0)
+        if rank == 0:
+            gathered = torch.zeros((world, shard_px), dtype=torch.int32, device=dev)
+            local = gathered[0]
+            gather_list = [gathered[i] for i in range(world)]
+        else:
+            local = torch.zeros((shard_px,), dtype=torch.int32, device=dev)
+            gather_list = None
+        peer_frame_ptr = None
+        if args.gather == "peer":
+            handle = torch.zeros(64, dtype=torch.uint8)
+            if rank == 0:
+                import ctypes as C
+                hb = (C.c_uint8 * 64)()
+                rc = lb.lib().lolb200_ipc_export(frame.data_ptr(), C.byref(hb))
+                assert rc == 0, lb.lib().lolb200_last_error()
+                handle = torch.tensor(list(hb), dtype=torch.uint8)
+            hdev = handle.to(dev)
+            dist.broadcast(hdev, 0)
+            if rank == 0:
+                peer_frame_ptr = frame.data_ptr()
+            else:
+                import ctypes as C
+                hb = (C.c_uint8 * 64)(*hdev.cpu().tolist())
+                p = C.c_void_p()
+                rc = lb.lib().lolb200_ipc_open(C.byref(hb), C.byref(p))
+                assert rc == 0, lb.lib().lolb200_last_error()
+                peer_frame_ptr = p.value
+            shard = lb.Shard(rank=rank, world=world, band_rows=0, dst_full_frame=1)
+            token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    launches = [0]
+
+    def step():
+        """One frame, complete on rank 0's HBM when the stream drains."""
+        if world == 1:
+            renderer.render_device(frame.data_ptr(), w, h, stream=stream)
+            launches[0] += 1
+        elif args.gather == "peer":
+            renderer.render_device(peer_frame_ptr, w, h, shard=shard, pitch_px=w, stream=stream)
+            launches[0] += 1
+            dist.all_reduce(token)  # every rank's stores are done before rank 0 goes on
+        else:
+            renderer.render_device(local.data_ptr(), w, h, shard=shard, pitch_px=w, stream=stream)
+            launches[0] += 1
+            dist.gather(local, gather_list, dst=0)
+            if rank == 0:
+                lb.deinterleave(gathered.data_ptr(), frame.data_ptr(), w, h, world, shard_px,
+                                stream=stream)
+                launches[0] += 1
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(W, 3)):
+        step()
+    sync_all()
+
+    # ---- timed region: K steps, device time, L2 flushed between steps (untimed) ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches[0] = 0
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+        sync_all()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    n_launches = launches[0]
+
+    # kernel-only duration (the render kernel alone), for the roofline
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        kev[i][0].record()
+        if world == 1:
+            renderer.render_device(frame.data_ptr(), w, h, stream=stream)
+        else:
+            renderer.render_device(local.data_ptr() if args.gather != "peer" else peer_frame_ptr,
+                                   w, h, shard=shard, pitch_px=w, stream=stream)
+        kev[i][1].record()
+    sync_all()
+    kernel_ms = float(sum(a.elapsed_time(b) for a, b in kev)) / K
+
+    if world > 1:
+        t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / K
+    value = w * h / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host buffers, D2H inside the timed region ----
+    host = torch.empty((h, w), dtype=torch.int32).pin_memory() if rank == 0 else None
+
+    def e2e_step():
+        if world == 1:
+            renderer.render_host(host.data_ptr(), w, h)
+        else:
+            step()
+            if rank == 0:
+                host.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) / K * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e_value = w * h / (e2e_ms * 1e-3) / 1e6
+
+    # ---- executed work (instrumented twin of the kernel, untimed) ----
+    copt = lb.Options.default(variant=args.variant, arith=1 if args.arith == "fast" else 0, counters=1)
+    crend = lb.Renderer(scene, copt, device=local_rank)
+    scratch = torch.zeros((h, w) if world == 1 else (shard_px,), dtype=torch.int32, device=dev)
+    crend.render_device(scratch.data_ptr(), w, h, pitch_px=w,
+                        shard=None if world == 1 else lb.Shard(rank=rank, world=world), stream=stream)
+    torch.cuda.synchronize()
+    cnt = crend.read_counters()
+    f_sdf = scene.flops_per_eval()
+    n_lights = scene.struct.n_lights
+    exec_flops = flops_model(f_sdf, n_lights, cnt["pixels"], cnt["primary_evals"], cnt["normal_evals"],
+                             cnt["shadow_evals"], cnt["normal_evals"] // 4, cnt["shadow_rays"],
+                             cnt["shadow_rays_culled"])
+    if world > 1:
+        t = torch.tensor([exec_flops], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the slowest rank bounds the frame
+        exec_flops = float(t[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak_tf, _ = lb.measure_fp32_peak(local_rank)
+    achieved_tf = exec_flops / (kernel_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp32", "kernel": "lol_render (NVRTC, per scene)",
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+        "peak_source": "measured here: lolb200_measure_fp32_peak (independent FFMA chains); "
+                       "MEASURED_PEAKS.json has no FP32 entry; nominal 74.45",
+        "frac_of_nominal": achieved_tf / FP32_NOMINAL_TFLOPS,
+        "flop_per_launch_executed": exec_flops, "kernel_ms": kernel_ms,
+        "traffic": None,
+        "hbm_write_gbs": (w * h * 4 / world) / (kernel_ms * 1e-3) / 1e9,
+    }
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roofline["hbm_frac_of_measured"] = roofline["hbm_write_gbs"] / peaks["hbm_gbs"]
+    except Exception:
+        pass
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms_per_step, "ms_per_frame": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.scene}.lol at {w}x{h}, one primary ray per pixel, frame complete "
+                               f"in rank 0's HBM", "arith": args.arith, "variant": args.variant,
+                   "sharding": "single GPU" if world == 1 else f"4-row bands cyclic over {world} ranks, "
+                               f"gather={args.gather}",
+                   "l2": "256 MB write between timed steps (untimed); the kernel reads no global inputs",
+                   "kernel": renderer.kernel_info()},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
+                "h2d_bytes_per_step": 192, "d2h_bytes_per_step": w * h * 4},
+        "gpu_launches": n_launches,
+        "roofline": roofline,
+        "clocks": clocks.summary(),
+        "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
+        "executed_evals_per_pixel": {k: cnt[k] / max(1, cnt["pixels"]) for k in
+                                     ("primary_evals", "normal_evals", "shadow_evals")},
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        # ~20 core-seconds on scene4: every 4th scanline of the same frame
+        stride = 4 if args.scene != "synthetic" else 64
+        ms, rays, kind, cores, totals = cpu_sample(args.scene, w, h, stride)
+        cpu_value = rays / (ms * 1e-3) / 1e6
+        out["cpu_baseline"] = {
+            "value": cpu_value, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "sample": f"every {stride}th scanline of the same {w}x{h} frame ({rays} rays, {ms:.0f} ms "
+                      f"wall), {cores} threads",
+            "ms_per_frame_extrapolated": ms * (w * h / rays),
+        }
+        scale = w * h / rays
+        ref_flops = flops_model(f_sdf, n_lights, w * h, totals["primary"] * scale, totals["normal"] * scale,
+                                totals["shadow"] * scale, w * h, w * h * n_lights, 0)
+        roofline["achieved_reference_work"] = ref_flops / (kernel_ms * 1e-3) / 1e12
+        roofline["flop_per_launch_reference"] = ref_flops
+
+    if args.all_scenes and world == 1:
+        per = {}
+        for name in ("scene", "scene2", "scene3", "scene4"):
+            r2 = lb.Renderer(load_scene(lb, name), opt, device=local_rank)
+            for _ in range(3):
+                r2.render_device(frame.data_ptr(), w, h, stream=stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                r2.render_device(frame.data_ptr(), w, h, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            per[name] = {"ms_per_frame": ms, "mrays_s": w * h / ms / 1e3}
+            r2.close()
+        out["per_scene"] = per
+
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
