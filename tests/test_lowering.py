@@ -1,0 +1,152 @@
+"""The code generator (lol_lower.c) without a GPU: structure of the emitted CUDA,
+NVRTC cross-compilation for sm_100a, and the generated distance function itself,
+compiled for the CPU with a tiny shim and compared with the oracle bit for bit."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import EXAMPLES, ROOT
+
+SHIM = r"""
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __constant__ static const
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline float __saturatef(float v) { return std::fmin(std::fmax(v, 0.f), 1.f); }
+static inline float lol_fma(float a, float b, float c) { return std::fma(a, b, c); }
+#define __fmaf_rn lol_fma
+static inline int __float2int_rz(float f) { return (int)f; }
+"""
+
+
+def cpu_sdf(tmp_path, src, tag):
+    """Compiles everything above the pipeline (helpers + generated lol_sdf) for the host."""
+    head = src.split("//@@SCENE@@")[0]
+    cu = tmp_path / f"sdf_{tag}.cpp"
+    cu.write_text(SHIM + head + """
+extern "C" void eval(const float* p, int n, float* d, unsigned* id) {
+  for (int i = 0; i < n; ++i) d[i] = lol_sdf(p[3*i], p[3*i+1], p[3*i+2], id[i]);
+}
+""")
+    so = tmp_path / f"sdf_{tag}.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cu)])
+    return C.CDLL(str(so))
+
+
+def oracle_sdf(scene, pts):
+    d = np.zeros(len(pts), np.float32)
+    ids = np.zeros(len(pts), np.uint32)
+    for i, p in enumerate(pts):
+        pt = (C.c_float * 3)(*p.tolist())
+        dd, ii = C.c_float(), C.c_uint32()
+        ol.port().lolo_sdf(C.cast(scene._ptr, C.c_void_p), 0, C.byref(pt), C.byref(dd), C.byref(ii))
+        d[i], ids[i] = dd.value, ii.value
+    return d, ids
+
+
+def _scene(lb, name, scenes_dir):
+    from loltracer_b200 import scenegen
+    if name == "synthetic":
+        return lb.Scene.from_string(scenegen.synthetic_scene_text())
+    return lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+
+
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
+def test_generated_sdf_equals_oracle_on_cpu(name, scenes_dir, tmp_path):
+    """Each primitive and smooth union as the lowering emits it == sdf.h / float.h."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, name, scenes_dir)
+    src = lb.lower_cuda(scene)
+    L = cpu_sdf(tmp_path, src, name)
+    rng = np.random.default_rng(11)
+    n = 3000 if name != "synthetic" else 300
+    pts = np.concatenate([rng.uniform(-12, 12, (n, 3)), rng.normal(0, 2, (n, 3)) + [0, 1, -6]]).astype(np.float32)
+    d = np.zeros(len(pts), np.float32)
+    ids = np.zeros(len(pts), np.uint32)
+    L.eval(pts.ctypes.data_as(C.c_void_p), len(pts), d.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p))
+    wd, wi = oracle_sdf(scene, pts)
+    assert np.array_equal(d.view(np.uint32), wd.view(np.uint32))
+    assert np.array_equal(ids, wi)
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_lowered_source_structure(name, scenes_dir):
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, name, scenes_dir)
+    src = lb.lower_cuda(scene)
+    assert "#define LOL_EXACT 1" in src and "#define LOL_SKIP_MISS 1" in src  # examples: black material 0
+    assert "#define LOL_CULL 1" in src and "#define LOL_SHADOW_EARLY 1" in src
+    assert f"#define LOL_NLIGHTS {scene.struct.n_lights}" in src
+    assert src.count("// object ") == scene.struct.n_objects
+    assert 'extern "C" __global__' in src and "struct lol_params" in src
+    assert "switch (obj" not in src  # no per-node dispatch at run time
+    off = lb.lower_cuda(scene, lb.Options.default(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, arith=1))
+    for flag in ("LOL_EXACT", "LOL_SKIP_MISS", "LOL_CULL", "LOL_SHADOW_EARLY"):
+        assert f"#define {flag} 0" in off
+
+
+def test_skips_are_licensed_by_the_scene(scenes_dir):
+    """The miss shortcut needs an all-zero material 0; the back-face cull needs finite
+    materials with shininess >= 0 (powf(0, negative) is inf)."""
+    import loltracer_b200 as lb
+
+    text = open(os.path.join(scenes_dir, "scene2.lol")).read()
+    lit = text.replace("ambient = (0, 0, 0)", "ambient = (0.1, 0, 0)", 1)
+    assert "#define LOL_SKIP_MISS 0" in lb.lower_cuda(lb.Scene.from_string(lit))
+    neg = text.replace("shininess = 50", "shininess = -2")
+    src = lb.lower_cuda(lb.Scene.from_string(neg))
+    assert "#define LOL_CULL 0" in src and "#define LOL_SKIP_MISS 1" in src
+
+
+def test_synthetic_scene_becomes_a_table_loop():
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
+    src = lb.lower_cuda(scene)
+    assert "lol_run0[]" in src and "128 x U(U(U(S,S),U(S,S)),U(U(S,S),U(S,S)))" in src
+    assert src.count("lol_len(") < 40  # one unrolled tree, not 1024 spheres
+    unrolled = lb.lower_cuda(scene, lb.Options.default(loop_threshold=100000))
+    assert unrolled.count("lol_len(") > 1024
+
+
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
+@pytest.mark.parametrize("arith", [0, 1])
+def test_nvrtc_compiles_for_sm_100a(name, arith, scenes_dir, tmp_path):
+    """Cross-compiles here; checks the image is an sm_100a cubin with no spills."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, name, scenes_dir)
+    opt = lb.Options.default(arith=arith)
+    image = lb.compile_cubin(lb.lower_cuda(scene, opt), opt)
+    assert image[:4] == b"\x7fELF"
+    path = tmp_path / "k.cubin"
+    path.write_bytes(image)
+    out = subprocess.run(["cuobjdump", "-res-usage", str(path)], capture_output=True, text=True).stdout
+    assert "lol_render" in out
+    m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out)
+    assert m, out
+    assert int(m.group(4)) == 0, "local memory (spills) in the render kernel"
+    sass = subprocess.run(["cuobjdump", "-sass", str(path)], capture_output=True, text=True).stdout
+    assert "code for sm_100a" in sass
+    if arith == 0:
+        assert "MUFU.RSQ" in sass  # IEEE sqrt = RSQ + Newton fix-up
+    assert "ATOMG" in sass or "ATOM" in sass  # the work counter
+
+
+def test_compile_error_is_reported():
+    import loltracer_b200 as lb
+
+    with pytest.raises(lb.LolB200Error) as e:
+        lb.compile_cubin("this is not CUDA")
+    assert e.value.code == -4 and "error" in str(e.value)
