@@ -11,9 +11,10 @@
  *
  * What it adds around the reference:
  *   - the four globals main.c defines (main.c:21-24);
- *   - a scene loader that replays our syntax tree through the reference's
- *     scene.c API in the order the bison actions call it (scene-parser.y:73-145);
- *     flex/bison are not installed, so scene_parse() itself cannot be generated;
+ *   - scene_parse() from loltracer_b200/backend/scene_parse_shim.c: our syntax
+ *     tree replayed through the reference's scene.c API in the order the bison
+ *     actions call it (scene-parser.y:73-145); flex/bison are not installed, so
+ *     the reference's own scene_parse() cannot be generated;
  *   - a headless replay of main.c's frame protocol (main.c:139-149,161,189-194,
  *     166-170,213) around the unmodified render_thread();
  *   - a per-pixel probe that calls the reference's static pipeline functions in
@@ -26,7 +27,6 @@
 #include "naive_renderer.c" /* the reference's, via -I/root/reference */
 
 #include "../loltracer_b200/backend/scene_translate.h"
-#include "../loltracer_b200/csrc/lol_ast.h"
 
 SDL_atomic_t exiting;
 SDL_atomic_t current_line;
@@ -35,83 +35,12 @@ SDL_sem* frame_exit_barrier;
 
 /* ---------------------------------------------------------------- loading -- */
 
-static struct vector* defs_from_node(const struct lol_node* n);
+/* scene_parse() / scene_parse_text(): our parser replayed through the
+ * reference's scene.c API (loltracer_b200/backend/scene_parse_shim.c). */
+struct scene* scene_parse(const char* filename);
+struct scene* scene_parse_text(const char* text, size_t len);
 
-static struct definition_value value_from_ast(const struct lol_value* v) {
-	struct definition_value out;
-	memset(&out, 0, sizeof out);
-	switch (v->kind) {
-	case LOL_V_NUM: /* scene-parser.y:129-132 */
-		out.type = VAL_NUM;
-		out.num = v->num;
-		break;
-	case LOL_V_LIST: /* scene-parser.y:133-136,148-160 */
-		out.type = VAL_LIST;
-		out.list = vector_new(float, 4);
-		for (size_t i = 0; i < v->nlist; i++)
-			vector_add(float, out.list) = v->list[i];
-		break;
-	case LOL_V_ID: /* scene-parser.y:137-140 */
-		out.type = VAL_ID;
-		out.id = v->id;
-		break;
-	case LOL_V_OBJ: { /* scene-parser.y:141-145 */
-		struct vector* defs = defs_from_node(v->obj);
-		out.type = VAL_OBJ;
-		out.obj = object_from_definition_list(v->obj->type, defs);
-		vector_free(defs, definition_free);
-		break;
-	}
-	}
-	return out;
-}
-
-static struct vector* defs_from_node(const struct lol_node* n) {
-	struct vector* defs = vector_new(struct definition, 16);
-	for (size_t i = 0; i < n->ndefs; i++) {
-		struct definition d;
-		d.prop = (enum property)n->defs[i].prop;
-		d.value = value_from_ast(&n->defs[i].value);
-		vector_add(struct definition, defs) = d;
-	}
-	return defs;
-}
-
-static struct scene* scene_from_doc(const struct lol_doc* doc) {
-	struct vector* materials = vector_new(struct material, 16);
-	struct scene* scene = NULL;
-
-	for (size_t i = 0; i < doc->nmaterials; i++) { /* scene-parser.y:89-103 */
-		struct vector* defs = defs_from_node(&doc->materials[i]);
-		vector_add(struct material, materials) = material_from_definition_list(defs);
-		vector_free(defs, definition_free);
-	}
-	for (size_t i = 0; i < doc->ncomponents; i++) { /* scene-parser.y:105-114 */
-		struct vector* defs = defs_from_node(&doc->components[i]);
-		if (!scene)
-			scene = scene_new();
-		scene_add_component_from_definition_list(scene, doc->components[i].type, defs);
-		vector_free(defs, definition_free);
-	}
-	if (!scene) {
-		vector_free(materials, NULL);
-		return NULL;
-	}
-	vector_free(scene->materials, NULL); /* scene-parser.y:74-77 */
-	scene->materials = materials;
-	return scene;
-}
-
-void* lolref_scene_load_string(const char* text, size_t len) {
-	char err[256];
-	struct lol_doc* doc = lol_parse_text(text, len, err, sizeof err);
-	struct scene* scene;
-	if (!doc) {
-		fprintf(stderr, "lolref: %s\n", err);
-		return NULL;
-	}
-	scene = scene_from_doc(doc);
-	lol_doc_free(doc);
+static void* checked(struct scene* scene) {
 	if (scene && !scene_validate_materials(scene)) { /* main.c:235 */
 		fprintf(stderr, "lolref: material index out of range\n");
 		scene_free(scene);
@@ -120,25 +49,8 @@ void* lolref_scene_load_string(const char* text, size_t len) {
 	return scene;
 }
 
-void* lolref_scene_load(const char* path) {
-	FILE* f = fopen(path, "rb");
-	char* buf;
-	long n;
-	void* scene;
-	if (!f)
-		return NULL;
-	fseek(f, 0, SEEK_END);
-	n = ftell(f);
-	fseek(f, 0, SEEK_SET);
-	buf = malloc((size_t)n + 1);
-	if (fread(buf, 1, (size_t)n, f) != (size_t)n)
-		n = 0;
-	buf[n] = 0;
-	fclose(f);
-	scene = lolref_scene_load_string(buf, (size_t)n);
-	free(buf);
-	return scene;
-}
+void* lolref_scene_load_string(const char* text, size_t len) { return checked(scene_parse_text(text, len)); }
+void* lolref_scene_load(const char* path) { return checked(scene_parse(path)); }
 
 void lolref_scene_free(void* scene) {
 	if (scene)

@@ -1,0 +1,48 @@
+"""The renderer.h drop-in (b200_renderer.c) under the headless twin of main.c."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+HOST = os.path.join(ROOT, "loltracer_b200", "backend", "build", "lol_headless_b200")
+
+
+@pytest.mark.parametrize("name,threads,size", [("scene", 1, (320, 240)), ("scene4", 8, (320, 240)),
+                                               ("scene3", 3, (1283, 721))])
+def test_backend_under_main_protocol(name, threads, size, scenes_dir, tmp_path):
+    import loltracer_b200 as lb
+
+    if not os.path.exists(HOST):
+        pytest.skip("headless host not built (needs the reference headers at build time)")
+    w, h = size
+    raw = tmp_path / "frame.bin"
+    path = os.path.join(scenes_dir, name + ".lol")
+    out = subprocess.run([HOST, str(threads), path, "--size", f"{w}x{h}", "--frames", "3", "--warmup", "1",
+                          "--raw", str(raw), "--verbose"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = np.fromfile(raw, np.uint32).reshape(h, w)
+    want = ol.port_render(lb.Scene.from_file(path), w, h)
+    hit = want["id"] != 0
+    assert ((got & 0xFFFFFF) != 0).sum() > 0
+    err = np.zeros(got.shape, np.int32)
+    for s in (16, 8, 0):
+        err = np.maximum(err, np.abs(((got >> s) & 0xFF).astype(np.int32) - ((want["rgba"] >> s) & 0xFF).astype(np.int32)))
+    assert err.max() <= 1 and err[~hit].max() == 0
+    assert "Frame 3" in out.stdout and "Cerrando" in out.stdout
+
+
+def test_backend_dumps_generated_code(scenes_dir, tmp_path):
+    """-j / --jitdump keeps its meaning: leave the generated code for a profiler."""
+    if not os.path.exists(HOST):
+        pytest.skip("headless host not built")
+    out = subprocess.run([HOST, "2", os.path.join(scenes_dir, "scene2.lol"), "-j", "--size", "64x48"],
+                         capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "lol_sdf" in (tmp_path / "lol-b200-kernel.cu").read_text()
+    assert (tmp_path / "lol-b200-kernel.cubin").read_bytes()[:4] == b"\x7fELF"

@@ -61,3 +61,179 @@ def test_examples_match_oracle(name, size, scenes_dir):
     _check(got, want)
     # the primary march takes exactly the reference's number of steps per pixel
     assert np.array_equal(got["nprimary"], want["nprimary"])
+
+
+@pytest.fixture(scope="module")
+def golden_frames():
+    from conftest import ROOT
+    return np.load(os.path.join(ROOT, "tests", "golden", "frames.npz"))
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("size", [(160, 90), (96, 64)])
+def test_examples_match_reference_goldens(name, size, scenes_dir, golden_frames):
+    """Straight against the reference's own output (tests/golden/frames.npz)."""
+    import loltracer_b200 as lb
+
+    w, h = size
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    got = _render(lb, scene, w, h)
+    key = f"{name}_{w}x{h}"
+    want = dict(rgba=golden_frames[key + "_rgba"], id=golden_frames[key + "_id"].astype(np.uint32),
+                dist=golden_frames[key + "_dist"])
+    _check(got, want)
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_examples_4k_match_oracle(name, scenes_dir):
+    """BASELINE size: every examples/*.lol scene at 3840x2160, every pixel."""
+    import loltracer_b200 as lb
+
+    w, h = 3840, 2160
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    got = _render(lb, scene, w, h)
+    want = ol.port_render(scene, w, h)
+    cmp = _check(got, want)
+    # powf differs between glibc and CUDA by an ulp or so: few pixels flip a channel by 1
+    assert cmp["n_rgb_off"] < 0.02 * w * h, cmp
+
+
+@pytest.mark.parametrize("k", [0, 16, 32, 48])
+def test_orbit_cameras(k, scenes_dir, golden_frames):
+    """Config C5: the camera is a per-frame argument, the kernel is not rebuilt."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
+    cam = scenegen.orbit_camera(scene.camera, k, 64)
+    got = _render(lb, scene, 160, 90, camera=cam)
+    key = f"orbit{k}_160x90"
+    _check(got, dict(rgba=golden_frames[key + "_rgba"], id=golden_frames[key + "_id"].astype(np.uint32),
+                     dist=golden_frames[key + "_dist"]))
+    got = _render(lb, scene, 1280, 720, camera=cam)
+    _check(got, ol.port_render(scene, 1280, 720, camera=cam))
+
+
+def test_synthetic_1024_primitives(golden_frames):
+    """Config C4: 128 smooth-union trees of 8 spheres, lowered to a table loop."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
+    got = _render(lb, scene, 96, 54)
+    _check(got, dict(rgba=golden_frames["synthetic_96x54_rgba"],
+                     id=golden_frames["synthetic_96x54_id"].astype(np.uint32),
+                     dist=golden_frames["synthetic_96x54_dist"]))
+    got = _render(lb, scene, 256, 144)
+    _check(got, ol.port_render(scene, 256, 144))
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (33, 3), (250, 131), (641, 2)])
+def test_ragged_sizes(size, scenes_dir):
+    """Frames that are not multiples of the 8x4 tile or of the work chunk."""
+    import loltracer_b200 as lb
+
+    w, h = size
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene.lol"))
+    _check(_render(lb, scene, w, h), ol.port_render(scene, w, h))
+
+
+def test_options_do_not_change_the_image(scenes_dir):
+    """The three exact shortcuts are exact: switching them off gives the same frame and
+    the reference's full shadow-march counts."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    w, h = 480, 270
+    want = ol.port_render(scene, w, h, counts=True)
+    on = _render(lb, scene, w, h)
+    off = _render(lb, scene, w, h, options=lb.Options.default(
+        skip_black_miss=0, cull_backfacing=0, shadow_early_out=0))
+    assert np.array_equal(on["rgba"], off["rgba"])
+    _check(off, want)
+    assert np.array_equal(off["nshadow"], want["nshadow"])  # nothing skipped
+    assert on["nshadow"].sum() < 0.7 * off["nshadow"].astype(np.int64).sum()
+
+
+def test_miss_pixels_shaded_when_material0_is_not_black(scenes_dir):
+    """naive_renderer.c shades misses with material 0; the shortcut must switch itself off."""
+    import loltracer_b200 as lb
+
+    text = open(os.path.join(scenes_dir, "scene2.lol")).read()
+    text = text.replace("ambient = (0, 0, 0)", "ambient = (0.3, 0.5, 0.7)", 1).replace(
+        "color = (0.01, 0.01, 0.01)", "color = (0.9, 0.9, 0.9)")
+    scene = lb.Scene.from_string(text)
+    w, h = 320, 180
+    got = _render(lb, scene, w, h)
+    want = ol.port_render(scene, w, h)
+    assert (want["rgba"][want["id"] == 0] & 0xFFFFFF).min() > 0  # misses are not black here
+    cmp = ol.compare_frames(got["rgba"], got["id"], want["rgba"], want["id"])
+    assert cmp["n_mask_off"] == 0 and cmp["max_rgb_err"] <= 1
+    miss = want["id"] == 0
+    d = np.abs(((got["rgba"][miss] >> 8) & 0xFF).astype(int) - ((want["rgba"][miss] >> 8) & 0xFF).astype(int))
+    assert d.max() <= 1
+
+
+def test_pixel_formats_and_pitch(scenes_dir):
+    """SDL_MapRGB for other 32-bit layouts (renderer.h:17-22) and a padded surface pitch."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene.lol"))
+    w, h = 200, 100
+    r = lb.Renderer(scene)
+    base = np.zeros((h, w), np.uint32)
+    r.render_host(base.ctypes.data, w, h)
+    # BGRX: r<<8 | g<<16 | b<<24, no alpha
+    f = lb.PixFmt(rshift=8, gshift=16, bshift=24, amask=0)
+    other = np.zeros((h, w), np.uint32)
+    r.render_host(other.ctypes.data, w, h, fmt=f)
+    rr, gg, bb = (base >> 16) & 0xFF, (base >> 8) & 0xFF, base & 0xFF
+    assert np.array_equal(other, (rr << 8) | (gg << 16) | (bb << 24))
+    # RGB565-style loss in a 32-bit word
+    f = lb.PixFmt(rshift=11, gshift=5, bshift=0, rloss=3, gloss=2, bloss=3, amask=0)
+    r.render_host(other.ctypes.data, w, h, fmt=f)
+    assert np.array_equal(other, ((rr >> 3) << 11) | ((gg >> 2) << 5) | (bb >> 3))
+    # pitch larger than the row: bytes beyond w stay untouched
+    pitch_px = w + 24
+    padded = np.full((h, pitch_px), 0xDEADBEEF, np.uint32)
+    r.render_host(padded.ctypes.data, w, h, pitch_bytes=pitch_px * 4)
+    assert np.array_equal(padded[:, :w], base) and (padded[:, w:] == 0xDEADBEEF).all()
+    r.close()
+
+
+def test_counters_match_oracle_when_nothing_is_skipped(scenes_dir):
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene2.lol"))
+    w, h = 640, 360
+    opt = lb.Options.default(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, counters=1)
+    r = lb.Renderer(scene, opt)
+    frame = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+    r.render_device(frame.data_ptr(), w, h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    c = r.read_counters()
+    t = ol.port_render(scene, w, h)["totals"]
+    assert (c["primary_evals"], c["normal_evals"], c["shadow_evals"], c["hit_pixels"], c["pixels"]) == (
+        t["primary"], t["normal"], t["shadow"], t["hits"], w * h)
+    r.close()
+
+
+def test_frames_are_repeatable_and_counter_rearms(scenes_dir):
+    """The work counter is reset by the last CTA: frame after frame, size after size."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene2.lol"))
+    r = lb.Renderer(scene)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for (w, h) in [(320, 240), (1920, 1080), (320, 240), (64, 64), (320, 240)]:
+        frame = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+        for _ in range(3):
+            frame.zero_()
+            r.render_device(frame.data_ptr(), w, h, stream=st)
+        torch.cuda.synchronize()
+        if (w, h) == (320, 240):
+            outs.append(frame.cpu().numpy())
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
+    assert (outs[0] != 0).all()
+    r.close()
