@@ -160,7 +160,14 @@ typedef struct lolb200_options {
 	int32_t loop_threshold;  /* top-level runs of >= this many same-shape
 	                            objects become a loop over __constant__ tables;
 	                            0 = default (16)                                */
-	int32_t reserved[9];
+	int32_t guarded_fastpath;/* exact mode only.  1: sqrt and the division by a
+	                            smoothness constant run without their per-
+	                            operation special-case branches, under one range
+	                            guard per sdf() evaluation that falls back to
+	                            the IEEE forms; results are bit-identical.
+	                            1 = where it pays (>= 3 spheres or a smooth
+	                            union), 2 = always, 0 = never                   */
+	int32_t reserved[8];
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

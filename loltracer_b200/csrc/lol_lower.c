@@ -90,6 +90,8 @@ struct cgen {
 	struct sb* out;
 	int tmp;      /* next temporary number                      */
 	int in_loop;  /* 1: constants are c[j], gathered into row[] */
+	int fast;     /* 1: guarded fast forms (lol_sqrt_fast, lol_smin_c) */
+	int div_ok;   /* 1: every smoothness passed the constant-division proof */
 	float* row;
 	size_t nrow, caprow;
 	const char* indent;
@@ -106,6 +108,19 @@ static void cst(struct cgen* g, float v) {
 	}
 	sb_printf(g->out, "LOL_TF(c[%zu])", g->nrow);
 	g->row[g->nrow++] = v;
+}
+
+/* Reserves the table slot of a constant this variant of the code does not read,
+ * so that the guarded and the reference function share one row layout. */
+static void cst_skip(struct cgen* g, float v) {
+	struct sb nowhere = {0};
+	struct sb* keep = g->out;
+	if (!g->in_loop)
+		return;
+	g->out = &nowhere;
+	cst(g, v);
+	g->out = keep;
+	free(nowhere.p);
 }
 
 static int is_pos_zero(float v) { return f2u(v) == 0u; }
@@ -129,6 +144,22 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 	switch (o->type) {
 	case LOLB200_OBJ_SPHERE: /* sdSphere, sdf.h:8-10 */
 		me = g->tmp++;
+		if (g->fast) {
+			/* same operations; the squared length also feeds the range guard */
+			sb_printf(g->out, "%sconst float qx%d = ", g->indent, me);
+			coord_minus(g, "x", o->point[0]);
+			sb_printf(g->out, ", qy%d = ", me);
+			coord_minus(g, "y", o->point[1]);
+			sb_printf(g->out, ", qz%d = ", me);
+			coord_minus(g, "z", o->point[2]);
+			sb_printf(g->out, ";\n%sconst float s%d = lol_dot(qx%d, qy%d, qz%d, qx%d, qy%d, qz%d);\n",
+			          g->indent, me, me, me, me, me, me, me);
+			sb_printf(g->out, "%slo = fminf(lo, s%d);\n", g->indent, me);
+			sb_printf(g->out, "%sconst float t%d = lol_sqrt_fast(s%d) - ", g->indent, me, me);
+			cst(g, o->radius);
+			sb_printf(g->out, ";\n");
+			return me;
+		}
 		sb_printf(g->out, "%sconst float t%d = lol_len(", g->indent, me);
 		coord_minus(g, "x", o->point[0]);
 		sb_printf(g->out, ", ");
@@ -166,10 +197,20 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 	default: { /* sminf(a, b, k), naive_renderer.c:21-24 */
 		int a = emit_node(g, (uint32_t)o->a);
 		int b = emit_node(g, (uint32_t)o->b);
+		const float rk = 1.0f / o->smoothness;
 		me = g->tmp++;
-		sb_printf(g->out, "%sconst float t%d = lol_smin(t%d, t%d, ", g->indent, me, a, b);
-		cst(g, o->smoothness);
-		sb_printf(g->out, ");\n");
+		if (g->fast && g->div_ok) {
+			sb_printf(g->out, "%sconst float t%d = lol_smin_c(t%d, t%d, ", g->indent, me, a, b);
+			cst(g, o->smoothness);
+			sb_printf(g->out, ", ");
+			cst(g, rk);
+			sb_printf(g->out, ");\n");
+		} else {
+			sb_printf(g->out, "%sconst float t%d = lol_smin(t%d, t%d, ", g->indent, me, a, b);
+			cst(g, o->smoothness);
+			cst_skip(g, rk);
+			sb_printf(g->out, ");\n");
+		}
 		return me;
 	}
 	}
@@ -192,9 +233,15 @@ static void signature(const lolb200_scene* s, uint32_t idx, struct sb* out) {
 	}
 }
 
-static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold) {
+/* One distance function.  fast = 0: the reference form (IEEE sqrt and division as
+ * the compiler emits them), named `name`.  fast = 1: the guarded form, which
+ * runs the same arithmetic without the per-operation special-case branches and
+ * hands the whole evaluation to `fallback` when its one range check fails. */
+static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_scene* s,
+                        int loop_threshold, const char* name, const char* attrs, int fast,
+                        int div_ok, const char* fallback) {
 	struct sb body = {0}, tables = {0};
-	struct cgen g = {.s = s, .out = &body};
+	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok};
 	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
 	size_t table_bytes = 0;
 	int run_no = 0;
@@ -205,13 +252,25 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold)
 		sigs[i] = sig.p;
 	}
 
+	/* The out-of-line fallback hands (distance, id) back in one 64-bit register
+	 * pair; a reference parameter would force the caller's id onto the stack. */
+	const int packed = strcmp(name, "lol_sdf") != 0;
 	sb_printf(&body,
 	          "// sdf (naive_renderer.c:30-44): running strict-< minimum over the top-level\n"
-	          "// objects, ids 1..n in file order, (INF, 0) when nothing is closer.\n"
-	          "__device__ __forceinline__ float lol_sdf(const float x, const float y, const float z,\n"
-	          "                                         lol_u32& id) {\n"
-	          "\tfloat best = LOL_INF;\n"
-	          "\tlol_u32 bid = 0u;\n");
+	          "// objects, ids 1..n in file order, (INF, 0) when nothing is closer.\n");
+	if (packed)
+		sb_printf(&body, "__device__ %s lol_u64 %s(const float x, const float y, const float z) {\n",
+		          attrs, name);
+	else
+		sb_printf(&body,
+		          "__device__ %s float %s(const float x, const float y, const float z,\n"
+		          "                                         lol_u32& id) {\n",
+		          attrs, name);
+	sb_printf(&body, "\tfloat best = LOL_INF;\n\tlol_u32 bid = 0u;\n");
+	if (fast)
+		sb_printf(&body,
+		          "\t// One range guard per evaluation: lo = min(every sqrt argument, 2^60 - max|p|).\n"
+		          "\tfloat lo = LOL_COORD_MAX - fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));\n");
 
 	for (uint32_t i = 0; i < s->n_objects;) {
 		uint32_t j = i + 1;
@@ -225,7 +284,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold)
 			for (uint32_t k = i; k < j; k++) {
 				struct sb scratch = {0};
 				struct cgen r = {.s = s, .out = (k == i) ? &body : &scratch, .in_loop = 1,
-				                 .indent = "\t\t"};
+				                 .indent = "\t\t", .fast = fast, .div_ok = div_ok};
 				if (k == i) {
 					sb_printf(&body, "#pragma unroll 2\n\tfor (int i = 0; i < %u; ++i) {\n",
 					          j - i);
@@ -265,19 +324,153 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold)
 		}
 		i = j;
 	}
-	sb_printf(&body, "\tid = bid;\n\treturn best;\n}\n");
+	if (fast)
+		sb_printf(&body,
+		          "\t// The fast forms are bit-identical to IEEE sqrt / division only inside\n"
+		          "\t// these ranges (DESIGN.md, guarded fast path); outside, redo it the long way.\n"
+		          "\tif (!(lo >= LOL_SQRT_FAST_MIN)) {\n"
+		          "\t\tconst lol_u64 r = %s(x, y, z);\n"
+		          "\t\tid = (lol_u32)(r >> 32);\n"
+		          "\t\treturn __uint_as_float((lol_u32)r);\n"
+		          "\t}\n",
+		          fallback);
+	if (packed)
+		sb_printf(&body, "\treturn ((lol_u64)bid << 32) | (lol_u64)__float_as_uint(best);\n}\n");
+	else
+		sb_printf(&body, "\tid = bid;\n\treturn best;\n}\n");
 
-	/* 64 KB of __constant__ space; keep a margin for the kernel parameters. */
-	sb_printf(out, "#define LOL_TABLE_SPACE %s\n",
-	          table_bytes <= 56 * 1024 ? "__constant__" : "__device__ const");
-	if (tables.p)
-		sb_putn(out, tables.p, tables.len);
+	if (tables_out) {
+		/* 64 KB of __constant__ space; keep a margin for the kernel parameters. */
+		sb_printf(tables_out, "#define LOL_TABLE_SPACE %s\n",
+		          table_bytes <= 56 * 1024 ? "__constant__" : "__device__ const");
+		if (tables.p)
+			sb_putn(tables_out, tables.p, tables.len);
+	}
 	sb_putn(out, body.p, body.len);
 
 	for (uint32_t i = 0; i < s->n_objects; i++)
 		free(sigs[i]);
 	free(sigs);
 	free(body.p);
+	free(tables.p);
+}
+
+/* ------------------------------------------------- guarded fast path proofs */
+
+/* Division by a scene constant without the divider's special-case branch:
+ *     q0 = n * rk;  r = fma(-k, q0, n);  q1 = fma(r, rk, q0);     rk = RN(1 / k)
+ * is the correctly rounded n / k for "almost all" k (Markstein); instead of
+ * relying on the theorem's side conditions the lowering PROVES it for the k at
+ * hand by trying all 2^23 significands of n.  Scaling n by a power of two scales
+ * q0, r and q1 exactly, so one binade covers every n whose intermediates stay
+ * normal; the kernel's range guard and the 0.5 + q rounding cover
+ * the rest. */
+__attribute__((target("fma"))) static int div_const_proof_fma(float k, float rk) {
+	for (uint32_t m = 0; m < (1u << 23); m++) {
+		uint32_t bits = 0x3f800000u | m;
+		float n, q0, r, q1;
+		memcpy(&n, &bits, 4);
+		q0 = n * rk;
+		r = __builtin_fmaf(-k, q0, n);
+		q1 = __builtin_fmaf(r, rk, q0);
+		if (q1 != n / k)
+			return 0;
+	}
+	return 1;
+}
+
+static int div_const_proof_soft(float k, float rk) {
+	for (uint32_t m = 0; m < (1u << 23); m++) {
+		uint32_t bits = 0x3f800000u | m;
+		float n, q0, r, q1;
+		memcpy(&n, &bits, 4);
+		q0 = n * rk;
+		r = fmaf(-k, q0, n);
+		q1 = fmaf(r, rk, q0);
+		if (q1 != n / k)
+			return 0;
+	}
+	return 1;
+}
+
+int lolb200_div_const_is_exact(float k) {
+	static _Thread_local float cache_k[8];
+	static _Thread_local int cache_ok[8], cache_n;
+	float rk;
+	int ok;
+	/* k in [2^-20, 2^20]: quotients of in-range numerators neither overflow nor
+	 * lose bits to underflow where 0.5 + q could still notice */
+	if (!(k >= 0x1p-20f && k <= 0x1p20f))
+		return 0;
+	for (int i = 0; i < cache_n; i++)
+		if (f2u(cache_k[i]) == f2u(k))
+			return cache_ok[i];
+	rk = 1.0f / k;
+	ok = __builtin_cpu_supports("fma") ? div_const_proof_fma(k, rk) : div_const_proof_soft(k, rk);
+	if (cache_n < 8) {
+		cache_k[cache_n] = k;
+		cache_ok[cache_n++] = ok;
+	}
+	return ok;
+}
+
+/* The guard checks |x|,|y|,|z| <= 2^60 at run time; with every centre, extent and
+ * radius below 2^60 too, each squared length stays finite (< 3 * 2^122) and every
+ * numerator of a smooth union stays far from overflow. */
+static int constants_in_range(const lolb200_scene* s) {
+	for (uint32_t i = 0; i < s->n_nodes; i++) {
+		const lolb200_object* o = &s->nodes[i];
+		const float v[8] = {o->point[0], o->point[1], o->point[2], o->radius,
+		                    o->point2[0], o->point2[1], o->point2[2], o->smoothness};
+		for (int k = 0; k < 8; k++)
+			if (!(fabsf(v[k]) <= 0x1p60f))
+				return 0;
+	}
+	return 1;
+}
+
+static int all_divisions_provable(const lolb200_scene* s) {
+	for (uint32_t i = 0; i < s->n_nodes; i++)
+		if (s->nodes[i].type == LOLB200_OBJ_SMOOTH_UNION &&
+		    !lolb200_div_const_is_exact(s->nodes[i].smoothness))
+			return 0;
+	return 1;
+}
+
+/* Measured on B200: the guard costs about as much as it removes when
+ * a scene has one or two spheres and no smooth union; from three spheres or one
+ * smooth union (a division) on it wins.  guarded_fastpath = 2 forces it. */
+static int guard_pays(const lolb200_scene* s) {
+	uint32_t spheres = 0, unions = 0;
+	for (uint32_t i = 0; i < s->n_nodes; i++) {
+		spheres += s->nodes[i].type == LOLB200_OBJ_SPHERE;
+		unions += s->nodes[i].type == LOLB200_OBJ_SMOOTH_UNION;
+	}
+	return unions >= 1 || spheres >= 3;
+}
+
+static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded) {
+	struct sb tables = {0};
+	if (guarded == 1 && !guard_pays(s))
+		guarded = 0;
+	if (guarded && constants_in_range(s)) {
+		struct sb ref = {0};
+		int div_ok = all_divisions_provable(s);
+		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
+		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL);
+		sb_putn(out, tables.p, tables.len);
+		sb_putn(out, ref.p, ref.len);
+		emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf", "__forceinline__", 1, div_ok,
+		            "lol_sdf_ref");
+		free(ref.p);
+	} else {
+		struct sb fn = {0};
+		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
+		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL);
+		sb_putn(out, tables.p, tables.len);
+		sb_putn(out, fn.p, fn.len);
+		free(fn.p);
+	}
 	free(tables.p);
 }
 
@@ -418,7 +611,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_params_text, strlen(lol_params_text));
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
-	emit_sdf(&out, s, threshold);
+	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

@@ -95,6 +95,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->skip_black_miss = 1;
 	o->cull_backfacing = 1;
 	o->shadow_early_out = 1;
+	o->guarded_fastpath = 1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

@@ -13,14 +13,19 @@ import oracle_lib as ol
 from conftest import EXAMPLES, ROOT
 
 SHIM = r"""
+#define LOL_HOST_SHIM 1
 #include <cmath>
 #include <cstring>
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
+typedef unsigned long long lol_u64_shim;
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 #define __constant__ static const
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
-static inline float __saturatef(float v) { return std::fmin(std::fmax(v, 0.f), 1.f); }
+static inline float __saturatef(float v) { return (v > 0.f) ? ((v < 1.f) ? v : 1.f) : 0.f; }
+static inline float lol_sqrt_fast(float x) { return std::sqrt(x); }
 static inline float lol_fma(float a, float b, float c) { return std::fma(a, b, c); }
 #define __fmaf_rn lol_fma
 static inline int __float2int_rz(float f) { return (int)f; }
@@ -65,7 +70,7 @@ def test_generated_sdf_equals_oracle_on_cpu(name, scenes_dir, tmp_path):
     import loltracer_b200 as lb
 
     scene = _scene(lb, name, scenes_dir)
-    src = lb.lower_cuda(scene)
+    src = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=2))
     L = cpu_sdf(tmp_path, src, name)
     rng = np.random.default_rng(11)
     n = 3000 if name != "synthetic" else 300
@@ -87,7 +92,14 @@ def test_lowered_source_structure(name, scenes_dir):
     assert "#define LOL_EXACT 1" in src and "#define LOL_SKIP_MISS 1" in src  # examples: black material 0
     assert "#define LOL_CULL 1" in src and "#define LOL_SHADOW_EARLY 1" in src
     assert f"#define LOL_NLIGHTS {scene.struct.n_lights}" in src
-    assert src.count("// object ") == scene.struct.n_objects
+    # the guarded fast form plus its out-of-line IEEE fallback (forced for scene.lol,
+    # whose two spheres and a box are below the "guard pays" threshold)
+    forced = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=2))
+    assert "#define LOL_GUARDED 1" in forced and "lol_sdf_ref" in forced
+    assert forced.count("// object ") == 2 * scene.struct.n_objects
+    assert ("#define LOL_GUARDED 1" in src) == (name != "scene")
+    plain = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=0))
+    assert "#define LOL_GUARDED 0" in plain and plain.count("// object ") == scene.struct.n_objects
     assert 'extern "C" __global__' in src and "struct lol_params" in src
     assert "switch (obj" not in src  # no per-node dispatch at run time
     off = lb.lower_cuda(scene, lb.Options.default(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, arith=1))
@@ -115,7 +127,7 @@ def test_synthetic_scene_becomes_a_table_loop():
     scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
     src = lb.lower_cuda(scene)
     assert "lol_run0[]" in src and "128 x U(U(U(S,S),U(S,S)),U(U(S,S),U(S,S)))" in src
-    assert src.count("lol_len(") < 40  # one unrolled tree, not 1024 spheres
+    assert src.count("lol_len(") + src.count("lol_sqrt_fast(") < 40  # one unrolled tree, not 1024 spheres
     unrolled = lb.lower_cuda(scene, lb.Options.default(loop_threshold=100000))
     assert unrolled.count("lol_len(") > 1024
 

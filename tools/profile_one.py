@@ -15,7 +15,8 @@ if name == "synthetic":
     scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
 else:
     scene = lb.Scene.from_file(os.path.join(ROOT, "tests", "golden", "scenes", name + ".lol"))
-r = lb.Renderer(scene, lb.Options.default(variant=variant, arith=arith))
+extra = dict(kv.split("=") for kv in os.environ.get("LOL_OPTS", "").split(",") if kv)
+r = lb.Renderer(scene, lb.Options.default(variant=variant, arith=arith, **{k: int(v) for k, v in extra.items()}))
 frame = torch.zeros((h, w), dtype=torch.int32, device="cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 st = torch.cuda.current_stream().cuda_stream
