@@ -57,6 +57,8 @@ struct DeviceGuard {
 
 } // namespace
 
+#define LOL_MAX_SLABS 8
+
 struct lolb200_renderer {
 	int device = 0;
 	lolb200_options opt{};
@@ -74,8 +76,13 @@ struct lolb200_renderer {
 	lol_u32* frame = nullptr;
 	size_t frame_pixels = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr; /* read-back of finished slabs */
+	cudaStream_t slab_stream[LOL_MAX_SLABS] = {}; /* slab k's launch: they may overlap */
+	cudaEvent_t slab_done[LOL_MAX_SLABS] = {};
 	void* registered = nullptr; /* host surface pinned with cudaHostRegister */
 	size_t registered_bytes = 0;
+	void* registered_dev = nullptr; /* device view of the pinned surface (zero-copy) */
+	int host_mode = 0;              /* 0 copy after the kernel, 1 zero-copy stores */
 };
 
 /* ------------------------------------------------------------------ NVRTC -- */
@@ -167,6 +174,16 @@ extern "C" void lolb200_renderer_destroy(lolb200_renderer* r) {
 			cudaStreamSynchronize(r->stream);
 			cudaStreamDestroy(r->stream);
 		}
+		if (r->copy_stream) {
+			cudaStreamSynchronize(r->copy_stream);
+			cudaStreamDestroy(r->copy_stream);
+		}
+		for (cudaEvent_t e : r->slab_done)
+			if (e)
+				cudaEventDestroy(e);
+		for (cudaStream_t st : r->slab_stream)
+			if (st)
+				cudaStreamDestroy(st);
 		if (r->registered)
 			cudaHostUnregister(r->registered);
 		cudaFree(r->frame);
@@ -261,11 +278,25 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)r->kernel,
 	                                                         LOLB200_KERNEL_THREADS, 0));
 	r->blocks_per_sm = occ > 0 ? occ : 1;
-	CREATE_TRY(cudaMalloc(&r->counter, 2 * sizeof(lol_u32)));
-	CREATE_TRY(cudaMemset(r->counter, 0, 2 * sizeof(lol_u32)));
+	/* one (next chunk, finished CTAs) pair per slab, so slab launches may overlap */
+	CREATE_TRY(cudaMalloc(&r->counter, 2 * LOL_MAX_SLABS * sizeof(lol_u32)));
+	CREATE_TRY(cudaMemset(r->counter, 0, 2 * LOL_MAX_SLABS * sizeof(lol_u32)));
 	CREATE_TRY(cudaMalloc(&r->stats, 8 * sizeof(lol_u64)));
 	CREATE_TRY(cudaMemset(r->stats, 0, 8 * sizeof(lol_u64)));
 	CREATE_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+	for (cudaEvent_t& e : r->slab_done)
+		CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	{
+		int lo = 0, hi = 0; /* earlier slabs get the higher priority: they must finish first */
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		for (int k = 0; k < LOL_MAX_SLABS; ++k) {
+			int prio = hi + k;
+			if (prio > lo)
+				prio = lo;
+			CREATE_TRY(cudaStreamCreateWithPriority(&r->slab_stream[k], cudaStreamNonBlocking, prio));
+		}
+	}
 #undef CREATE_TRY
 	*out = r;
 	return LOLB200_OK;
@@ -316,10 +347,12 @@ static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands
 	return 8;
 }
 
-extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
-                                     const lolb200_pixfmt* fmt, const lolb200_shard* shard,
-                                     void* dst_dev, size_t pitch_px, const lolb200_aux* aux,
-                                     void* stream) {
+/* One launch over local bands [band_begin, band_begin + band_count) of the
+ * rank's share (band_count = 0: all of them). */
+static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                        const lolb200_pixfmt* fmt, const lolb200_shard* shard, void* dst_dev,
+                        size_t pitch_px, const lolb200_aux* aux, void* stream, size_t band_begin,
+                        size_t band_count, int counter_slot) {
 	if (!r || !dst_dev || w <= 0 || h <= 0 || pitch_px < (size_t)w) {
 		lolb200_set_error("lolb200_render_device: bad argument");
 		return LOLB200_EINVAL;
@@ -345,10 +378,13 @@ extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* 
 	lolb200_camera_basis_compute(&c, w, h, &cb);
 
 	const size_t bands = ((size_t)h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
-	const size_t local_bands =
+	size_t local_bands =
 		bands > (size_t)sh.rank ? (bands - sh.rank + sh.world - 1) / sh.world : 0;
-	if (local_bands == 0)
+	if (band_begin >= local_bands)
 		return LOLB200_OK;
+	local_bands -= band_begin;
+	if (band_count && band_count < local_bands)
+		local_bands = band_count;
 
 	lol_params P;
 	memset(&P, 0, sizeof P);
@@ -369,10 +405,11 @@ extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* 
 	P.chunk_w = pick_chunk_w(r, w, local_bands);
 	P.chunks_per_band = (lol_u32)(((size_t)w + P.chunk_w - 1) / P.chunk_w);
 	P.n_chunks = (lol_u32)(P.chunks_per_band * local_bands);
+	P.band_begin = (lol_u32)band_begin;
 	P.rshift = pf.rshift; P.gshift = pf.gshift; P.bshift = pf.bshift;
 	P.rloss = pf.rloss;   P.gloss = pf.gloss;   P.bloss = pf.bloss;
 	P.amask = pf.amask;
-	P.counter = r->counter;
+	P.counter = r->counter + 2 * counter_slot;
 	P.dst = (lol_u32*)dst_dev;
 	if (aux) {
 		P.aux_dist = aux->dist;
@@ -393,6 +430,13 @@ extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* 
 	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3(LOLB200_KERNEL_THREADS),
 	                          args, 0, (cudaStream_t)stream));
 	return LOLB200_OK;
+}
+
+extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                                     const lolb200_pixfmt* fmt, const lolb200_shard* shard,
+                                     void* dst_dev, size_t pitch_px, const lolb200_aux* aux,
+                                     void* stream) {
+	return launch_bands(r, cam, w, h, fmt, shard, dst_dev, pitch_px, aux, stream, 0, 0, 0);
 }
 
 extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
@@ -418,20 +462,57 @@ extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* ca
 			cudaHostUnregister(r->registered);
 			r->registered = nullptr;
 		}
-		if (cudaHostRegister(pixels, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+		r->registered_dev = nullptr;
+		if (cudaHostRegister(pixels, bytes, cudaHostRegisterMapped) == cudaSuccess) {
 			r->registered = pixels;
 			r->registered_bytes = bytes;
+			if (cudaHostGetDevicePointer(&r->registered_dev, pixels, 0) != cudaSuccess) {
+				cudaGetLastError();
+				r->registered_dev = nullptr;
+			}
 		} else {
 			cudaGetLastError(); /* pageable copy still works, only slower */
 		}
 	}
-	int rc = lolb200_render_device(r, cam, w, h, fmt, nullptr, r->frame, (size_t)w, nullptr,
-	                               r->stream);
-	if (rc != LOLB200_OK)
-		return rc;
-	CUDA_TRY(cudaMemcpy2DAsync(pixels, pitch_bytes, r->frame, (size_t)w * 4, (size_t)w * 4, (size_t)h,
-	                           cudaMemcpyDeviceToHost, r->stream));
-	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	const char* mode = getenv("LOLB200_HOST_MODE");
+	if (mode && !strcmp(mode, "mapped") && r->registered_dev && pitch_bytes % 4 == 0) {
+		/* zero-copy: the kernel stores pixels straight into the pinned surface */
+		int rc0 = lolb200_render_device(r, cam, w, h, fmt, nullptr, r->registered_dev, pitch_bytes / 4,
+		                                nullptr, r->stream);
+		if (rc0 != LOLB200_OK)
+			return rc0;
+		CUDA_TRY(cudaStreamSynchronize(r->stream));
+		return LOLB200_OK;
+	}
+	/* The frame is rendered as a few slabs of bands, one launch each; while slab
+	 * k+1 renders, the copy engine moves slab k into the caller's surface, so the
+	 * frame costs about max(kernel, PCIe copy) plus one slab's copy instead of
+	 * their sum.  LOLB200_HOST_MODE=copy renders and copies the frame whole. */
+	const size_t bands = ((size_t)h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
+	size_t slabs = (mode && !strcmp(mode, "copy")) ? 1 : LOL_MAX_SLABS;
+	if (mode && !strncmp(mode, "slabs", 5) && atoi(mode + 5) > 0)
+		slabs = (size_t)atoi(mode + 5) <= LOL_MAX_SLABS ? (size_t)atoi(mode + 5) : LOL_MAX_SLABS;
+	if (bands < slabs * 16)
+		slabs = bands / 16 ? bands / 16 : 1;
+	const size_t per = (bands + slabs - 1) / slabs;
+	for (size_t k = 0, b0 = 0; b0 < bands; ++k, b0 += per) {
+		const size_t nb = b0 + per <= bands ? per : bands - b0;
+		const size_t y0 = b0 * LOL_BAND_ROWS;
+		const size_t rows = (y0 + nb * LOL_BAND_ROWS <= (size_t)h) ? nb * LOL_BAND_ROWS : (size_t)h - y0;
+		/* Slab launches go to separate streams with their own work counters: CTAs
+		 * of slab k+1 move in as those of slab k run out of chunks, so the frame
+		 * has one tail, not one per slab. */
+		int rc = launch_bands(r, cam, w, h, fmt, nullptr, r->frame, (size_t)w, nullptr,
+		                      r->slab_stream[k], b0, nb, (int)k);
+		if (rc != LOLB200_OK)
+			return rc;
+		CUDA_TRY(cudaEventRecord(r->slab_done[k], r->slab_stream[k]));
+		CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->slab_done[k], 0));
+		CUDA_TRY(cudaMemcpy2DAsync((char*)pixels + y0 * pitch_bytes, pitch_bytes, r->frame + y0 * w,
+		                           (size_t)w * 4, (size_t)w * 4, rows, cudaMemcpyDeviceToHost,
+		                           r->copy_stream));
+	}
+	CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
 	return LOLB200_OK;
 }
 

@@ -25,6 +25,7 @@ struct lol_params {
 	lol_u32 chunk_w;     // pixels per work chunk along x (multiple of 8)
 	lol_u32 chunks_per_band;
 	lol_u32 n_chunks;
+	lol_u32 band_begin;  // first local band of this launch (slabs of one frame)
 	lol_u32 rshift, gshift, bshift, rloss, gloss, bloss, amask;
 	lol_u32* counter;    // [0] next chunk, [1] finished CTAs
 	lol_u32* dst;
