@@ -70,6 +70,8 @@ struct lolb200_renderer {
 	int sm_count = 0;
 	int blocks_per_sm = 1;
 	int regs = 0, smem = 0, local = 0, max_threads = 0;
+	int variant = 1;
+	size_t dyn_smem = 0; /* variant 2: warp-private queues */
 	lol_u32* counter = nullptr; /* device: [0] next chunk, [1] finished CTAs */
 	lol_u64* stats = nullptr;   /* device: 8 accumulators (options.counters) */
 	/* render_host staging */
@@ -268,15 +270,28 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	r->sm_count = prop.multiProcessorCount;
 	CREATE_TRY(cudaLibraryLoadData(&r->lib, r->image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 	CREATE_TRY(cudaLibraryGetKernel(&r->kernel, r->lib, "lol_render"));
+	{
+		/* the lowering states what it generated */
+		const char* v = strstr(r->source.c_str(), "#define LOL_VARIANT ");
+		r->variant = v ? atoi(v + strlen("#define LOL_VARIANT ")) : 1;
+		const char* sm = strstr(r->source.c_str(), "#define LOL_SMEM_PER_WARP ");
+		if (r->variant == 2 && sm) {
+			r->dyn_smem = (size_t)atol(sm + strlen("#define LOL_SMEM_PER_WARP ")) *
+			              (LOLB200_KERNEL_THREADS / 32);
+			CREATE_TRY(cudaFuncSetAttribute((const void*)r->kernel,
+			                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)r->dyn_smem));
+		}
+	}
 	cudaFuncAttributes fa;
 	CREATE_TRY(cudaFuncGetAttributes(&fa, (const void*)r->kernel));
 	r->regs = fa.numRegs;
-	r->smem = (int)fa.sharedSizeBytes;
+	r->smem = (int)(fa.sharedSizeBytes + r->dyn_smem);
 	r->local = (int)fa.localSizeBytes;
 	r->max_threads = fa.maxThreadsPerBlock;
 	int occ = 0;
 	CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)r->kernel,
-	                                                         LOLB200_KERNEL_THREADS, 0));
+	                                                         LOLB200_KERNEL_THREADS, r->dyn_smem));
 	r->blocks_per_sm = occ > 0 ? occ : 1;
 	/* one (next chunk, finished CTAs) pair per slab, so slab launches may overlap */
 	CREATE_TRY(cudaMalloc(&r->counter, 2 * LOL_MAX_SLABS * sizeof(lol_u32)));
@@ -339,7 +354,7 @@ extern "C" size_t lolb200_shard_pixels(int w, int h, int world, int band_rows) {
  * one counter; narrow ones keep every warp busy when a shard is small. */
 static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands) {
 	const size_t warps = (size_t)r->sm_count * r->blocks_per_sm * (LOLB200_KERNEL_THREADS / 32);
-	for (lol_u32 cw = 64; cw > 8; cw >>= 1) {
+	for (lol_u32 cw = r->variant == 2 ? 32 : 64; cw > 8; cw >>= 1) {
 		size_t chunks = (((size_t)w + cw - 1) / cw) * local_bands;
 		if (chunks >= 16 * warps)
 			return cw;
@@ -428,7 +443,7 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 		grid = grid_needed;
 	void* args[] = {&P};
 	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3(LOLB200_KERNEL_THREADS),
-	                          args, 0, (cudaStream_t)stream));
+	                          args, r->dyn_smem, (cudaStream_t)stream));
 	return LOLB200_OK;
 }
 

@@ -18,6 +18,8 @@ int lolb200_div_const_is_exact(float k);
 
 /* Threads per CTA of the generated kernel (8 warps). */
 #define LOLB200_KERNEL_THREADS 256
+/* Kernel structure used when options.variant == 0 (1 phase-sequential, 2 compaction). */
+#define LOLB200_DEFAULT_VARIANT 1
 
 #ifdef __cplusplus
 }

@@ -582,7 +582,9 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		o = *opt;
 	else
 		lolb200_options_default(&o);
-	variant = o.variant ? o.variant : 1;
+	variant = o.variant ? o.variant : LOLB200_DEFAULT_VARIANT;
+	if (s->n_objects > 65535u)
+		variant = 1; /* variant 2 keeps object ids in 16 bits */
 	threshold = o.loop_threshold > 0 ? o.loop_threshold : 16;
 	if (variant != 1 && variant != 2) {
 		lolb200_set_error("unknown kernel variant %d", variant);
@@ -601,6 +603,13 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_printf(&out, "#define LOL_COUNTERS %d\n", o.counters != 0);
 	sb_printf(&out, "#define LOL_VARIANT %d\n", variant);
 	sb_printf(&out, "#define LOL_THREADS %d\n", LOLB200_KERNEL_THREADS);
+	if (variant == 2) {
+		/* struct lol_warp_smem (lol_kernel.cuh): p, n, t|px, dir, sh[lights], id,
+		 * hits, task (+ nsh in instrumented builds), 128 pixels per warp */
+		const unsigned lights = s->n_lights ? s->n_lights : 1;
+		sb_printf(&out, "#define LOL_SMEM_PER_WARP %u\n",
+		          4u * 128u * (3u + 3u + 1u + 4u + lights) + 128u * 4u + (o.counters ? 256u : 0u));
+	}
 
 	marker = strstr(lol_kernel_text, "//@@SCENE@@");
 	if (!marker) {

@@ -237,3 +237,61 @@ def test_frames_are_repeatable_and_counter_rearms(scenes_dir):
     assert all(np.array_equal(outs[0], o) for o in outs[1:])
     assert (outs[0] != 0).all()
     r.close()
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("guarded", [0, 2])
+def test_kernel_variants_are_bit_identical(name, variant, guarded, scenes_dir):
+    """Phase-sequential vs ray-compaction kernel, IEEE forms vs guarded fast path: the
+    same distance, id and primary step count for every pixel, and the oracle's pixels."""
+    import loltracer_b200 as lb
+
+    w, h = 1000, 562  # not a multiple of the 32x4 chunk
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    want = ol.port_render(scene, w, h, counts=True)
+    got = _render(lb, scene, w, h, options=lb.Options.default(variant=variant, guarded_fastpath=guarded))
+    _check(got, want)
+    assert np.array_equal(got["nprimary"], want["nprimary"])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_shadow_step_counts_per_variant(variant, scenes_dir):
+    """With the shortcuts off both kernels march exactly the reference's shadow steps."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
+    w, h = 400, 226
+    opt = lb.Options.default(variant=variant, skip_black_miss=0, cull_backfacing=0, shadow_early_out=0,
+                             counters=1)
+    got = _render(lb, scene, w, h, options=opt)
+    want = ol.port_render(scene, w, h, counts=True)
+    _check(got, want)
+    assert np.array_equal(got["nshadow"], want["nshadow"])
+    c = got["renderer"].read_counters()
+    t = want["totals"]
+    assert (c["primary_evals"], c["normal_evals"], c["shadow_evals"]) == (t["primary"], t["normal"], t["shadow"])
+
+
+@pytest.mark.parametrize("variant", [2])
+@pytest.mark.parametrize("world", [2, 8])
+def test_variant2_shards_and_small_chunks(variant, world, scenes_dir):
+    """Compaction kernel on shards (narrow chunks) and ragged frames."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    w, h = 333, 129
+    r = lb.Renderer(scene, lb.Options.default(variant=variant))
+    st = torch.cuda.current_stream().cuda_stream
+    frame = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+    for rank in range(world):
+        r.render_device(frame.data_ptr(), w, h, pitch_px=w,
+                        shard=lb.Shard(rank=rank, world=world, dst_full_frame=1), stream=st)
+    torch.cuda.synchronize()
+    want = ol.port_render(scene, w, h)
+    got = frame.cpu().numpy().view(np.uint32)
+    err = np.zeros(got.shape, np.int32)
+    for s in (16, 8, 0):
+        err = np.maximum(err, np.abs(((got >> s) & 0xFF).astype(np.int32) - ((want["rgba"] >> s) & 0xFF).astype(np.int32)))
+    assert err.max() <= 1 and err[want["id"] == 0].max() == 0
+    r.close()
