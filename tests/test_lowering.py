@@ -96,10 +96,10 @@ def test_lowered_source_structure(name, scenes_dir):
     # whose two spheres and a box are below the "guard pays" threshold)
     forced = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=2))
     assert "#define LOL_GUARDED 1" in forced and "lol_sdf_ref" in forced
-    assert forced.count("// object ") == 2 * scene.struct.n_objects
+    assert forced.count("{ // object ") == 2 * scene.struct.n_objects
     assert ("#define LOL_GUARDED 1" in src) == (name != "scene")
     plain = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=0))
-    assert "#define LOL_GUARDED 0" in plain and plain.count("// object ") == scene.struct.n_objects
+    assert "#define LOL_GUARDED 0" in plain and plain.count("{ // object ") == scene.struct.n_objects
     assert 'extern "C" __global__' in src and "struct lol_params" in src
     assert "switch (obj" not in src  # no per-node dispatch at run time
     off = lb.lower_cuda(scene, lb.Options.default(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, arith=1))
