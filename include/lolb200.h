@@ -167,7 +167,10 @@ typedef struct lolb200_options {
 	                            the IEEE forms; results are bit-identical.
 	                            1 = where it pays (>= 3 spheres or a smooth
 	                            union), 2 = always, 0 = never                   */
-	int32_t reserved[8];
+	int32_t prune_bounds;    /* 1: inside table loops an object is skipped when a
+	                            conservative bounding ball proves it cannot
+	                            beat the running minimum (exact)     */
+	int32_t reserved[7];
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

@@ -71,7 +71,8 @@ class Options(C.Structure):
     _fields_ = [("arith", C.c_int32), ("skip_black_miss", C.c_int32),
                 ("cull_backfacing", C.c_int32), ("shadow_early_out", C.c_int32),
                 ("counters", C.c_int32), ("variant", C.c_int32), ("loop_threshold", C.c_int32),
-                ("guarded_fastpath", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("guarded_fastpath", C.c_int32), ("prune_bounds", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
 
     @classmethod
     def default(cls, **kw) -> "Options":

@@ -233,13 +233,69 @@ static void signature(const lolb200_scene* s, uint32_t idx, struct sb* out) {
 	}
 }
 
+/* Conservative bounding ball of an object's distance field:
+ *     dist(obj, p) >= |p - C| - R      for every p (in exact arithmetic).
+ * sphere: (c, r).  rounded box: (c, |half extents| + r).  smooth union: the ball
+ * around both children's balls, grown by k/4 (sminf(a,b,k) >= min(a,b) - k/4,
+ * float.h:29-33).  A plane has no ball (returns 0).  Computed in double. */
+static int bound_node(const lolb200_scene* s, uint32_t idx, double C[3], double* R) {
+	const lolb200_object* o = &s->nodes[idx];
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE:
+		for (int k = 0; k < 3; k++)
+			C[k] = o->point[k];
+		*R = o->radius;
+		return isfinite(*R) && isfinite(C[0]) && isfinite(C[1]) && isfinite(C[2]);
+	case LOLB200_OBJ_BOX:
+		for (int k = 0; k < 3; k++)
+			C[k] = o->point[k];
+		*R = sqrt((double)o->point2[0] * o->point2[0] + (double)o->point2[1] * o->point2[1] +
+		          (double)o->point2[2] * o->point2[2]) + fabs((double)o->radius);
+		return isfinite(*R) && isfinite(C[0]) && isfinite(C[1]) && isfinite(C[2]);
+	case LOLB200_OBJ_PLANE: return 0;
+	default: {
+		double Ca[3], Cb[3], Ra, Rb, da = 0, db = 0;
+		if (!(o->smoothness >= 0.f) || !isfinite(o->smoothness))
+			return 0;
+		if (!bound_node(s, (uint32_t)o->a, Ca, &Ra) || !bound_node(s, (uint32_t)o->b, Cb, &Rb))
+			return 0;
+		for (int k = 0; k < 3; k++) {
+			C[k] = 0.5 * (Ca[k] + Cb[k]);
+			da += (Ca[k] - C[k]) * (Ca[k] - C[k]);
+			db += (Cb[k] - C[k]) * (Cb[k] - C[k]);
+		}
+		da = sqrt(da) + Ra;
+		db = sqrt(db) + Rb;
+		*R = (da > db ? da : db) + 0.25 * (double)o->smoothness;
+		return 1;
+	}
+	}
+}
+
+/* The ball as the kernel uses it: radius padded by 0.2 % plus 0.002 * (|C|_1 + 1)
+ * -- three orders of magnitude above the rounding error of the evaluated
+ * distance (a few ulps of the coordinates per tree level) -- and the kernel
+ * adds a relative 0.4 % on the distance side, so the test stays conservative at
+ * any scene scale.  Unboundable objects get R = +INF: never skipped. */
+static void bound_row(const lolb200_scene* s, uint32_t idx, float row[4]) {
+	double C[3], R;
+	if (!bound_node(s, idx, C, &R)) {
+		row[0] = row[1] = row[2] = 0.f;
+		row[3] = INFINITY;
+		return;
+	}
+	for (int k = 0; k < 3; k++)
+		row[k] = (float)C[k];
+	row[3] = (float)((R > 0 ? R : 0) * 1.002 + 0.002 * (fabs(C[0]) + fabs(C[1]) + fabs(C[2]) + 1.0) + 1e-6);
+}
+
 /* One distance function.  fast = 0: the reference form (IEEE sqrt and division as
  * the compiler emits them), named `name`.  fast = 1: the guarded form, which
  * runs the same arithmetic without the per-operation special-case branches and
  * hands the whole evaluation to `fallback` when its one range check fails. */
 static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_scene* s,
                         int loop_threshold, const char* name, const char* attrs, int fast,
-                        int div_ok, const char* fallback) {
+                        int div_ok, const char* fallback, int prune) {
 	struct sb body = {0}, tables = {0};
 	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok};
 	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
@@ -272,31 +328,84 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "\t// One range guard per evaluation: lo = min(every sqrt argument, 2^60 - max|p|).\n"
 		          "\tfloat lo = LOL_COORD_MAX - fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));\n");
 
+	/* Segments: maximal runs of same-shaped neighbours.  Long runs become table
+	 * loops.  With pruning the short segments are evaluated FIRST (they are cheap
+	 * and tighten `best`, which is what the loops' bounding-ball test compares
+	 * against); the update rule of a loop then breaks ties by object id, so the
+	 * result is the reference's "first of equal distances" whatever the order. */
+	for (int pass = 0; pass < 2; pass++)
 	for (uint32_t i = 0; i < s->n_objects;) {
 		uint32_t j = i + 1;
 		while (j < s->n_objects && strcmp(sigs[j], sigs[i]) == 0)
 			j++;
-		if ((int)(j - i) >= loop_threshold) {
+		const int is_loop = (int)(j - i) >= loop_threshold;
+		/* pass 0: what comes first; pass 1: the rest */
+		const int now = prune ? (pass == 0 ? !is_loop : is_loop) : (pass == 0);
+		if (!now) {
+			i = j;
+			continue;
+		}
+		if (is_loop) {
 			/* objects i .. j-1 share one shape: loop over a parameter table */
 			size_t per_row = 0;
+			int tie_aware = 0;
+			if (prune) /* was something with a larger id hoisted in front of this run? */
+				for (uint32_t a = i + 1; a < s->n_objects && !tie_aware;) {
+					uint32_t b = a + 1;
+					while (b < s->n_objects && strcmp(sigs[b], sigs[a]) == 0)
+						b++;
+					if ((int)(b - a) < loop_threshold && a > i)
+						tie_aware = 1;
+					a = b;
+				}
 			sb_printf(&body, "\t// objects %u..%u: %u x %s\n", i + 1, j, j - i, sigs[i]);
 			sb_printf(&tables, "LOL_TABLE_SPACE lol_u32 lol_run%d[] = {\n", run_no);
 			for (uint32_t k = i; k < j; k++) {
 				struct sb scratch = {0};
 				struct cgen r = {.s = s, .out = (k == i) ? &body : &scratch, .in_loop = 1,
 				                 .indent = "\t\t", .fast = fast, .div_ok = div_ok};
+				float ball[4];
 				if (k == i) {
-					sb_printf(&body, "#pragma unroll 2\n\tfor (int i = 0; i < %u; ++i) {\n",
+					sb_printf(&body, "#pragma unroll 1\n\tfor (int i = 0; i < %u; ++i) {\n",
 					          j - i);
 					sb_printf(&body, "\t\tconst lol_u32* c = lol_run%d + i * LOL_RUN%d_STRIDE;\n",
 					          run_no, run_no);
 				}
+				if (prune) {
+					/* row = ball (C, R), then the object's own constants */
+					bound_row(s, s->objects[k], ball);
+					if (k == i)
+						sb_printf(&body,
+						          "\t\t{ // dist(object, p) >= |p - C| - R >= best: cannot win\n"
+						          "\t\t\tconst float bx = x - ");
+					cst(&r, ball[0]);
+					if (k == i)
+						sb_printf(&body, ", by = y - ");
+					cst(&r, ball[1]);
+					if (k == i)
+						sb_printf(&body, ", bz = z - ");
+					cst(&r, ball[2]);
+					if (k == i)
+						sb_printf(&body, ";\n\t\t\tconst float u = (best + ");
+					cst(&r, ball[3]);
+					if (k == i)
+						sb_printf(&body,
+						          ") * LOL_F(0x3f808312 /*1.004*/);\n"
+						          "\t\t\tif (u <= 0.f || lol_dot(bx, by, bz, bx, by, bz) > u * u)\n"
+						          "\t\t\t\tcontinue;\n\t\t}\n");
+				}
 				int t = emit_node(&r, s->objects[k]);
 				if (k == i) {
-					sb_printf(&body,
-					          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu + "
-					          "(lol_u32)i;\n\t\t}\n\t}\n",
-					          t, t, i + 1);
+					if (tie_aware)
+						sb_printf(&body,
+						          "\t\tif (t%d < best || (t%d == best && %uu + (lol_u32)i < bid)) {\n"
+						          "\t\t\tbest = t%d;\n\t\t\tbid = %uu + (lol_u32)i;\n\t\t}\n\t}\n",
+						          t, t, i + 1, t, i + 1);
+					else
+						sb_printf(&body,
+						          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu + "
+						          "(lol_u32)i;\n\t\t}\n\t}\n",
+						          t, t, i + 1);
 					per_row = r.nrow;
 				}
 				sb_printf(&tables, "\t");
@@ -449,7 +558,8 @@ static int guard_pays(const lolb200_scene* s) {
 	return unions >= 1 || spheres >= 3;
 }
 
-static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded) {
+static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
+                     int prune) {
 	struct sb tables = {0};
 	if (guarded == 1 && !guard_pays(s))
 		guarded = 0;
@@ -457,16 +567,16 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		struct sb ref = {0};
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
-		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL);
+		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
 		emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf", "__forceinline__", 1, div_ok,
-		            "lol_sdf_ref");
+		            "lol_sdf_ref", prune);
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
 		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
-		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL);
+		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
@@ -620,7 +730,8 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_params_text, strlen(lol_params_text));
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
-	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0);
+	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
+	         o.prune_bounds != 0);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

@@ -96,6 +96,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->cull_backfacing = 1;
 	o->shadow_early_out = 1;
 	o->guarded_fastpath = 1;
+	o->prune_bounds = 1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

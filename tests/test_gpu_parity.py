@@ -295,3 +295,22 @@ def test_variant2_shards_and_small_chunks(variant, world, scenes_dir):
         err = np.maximum(err, np.abs(((got >> s) & 0xFF).astype(np.int32) - ((want["rgba"] >> s) & 0xFF).astype(np.int32)))
     assert err.max() <= 1 and err[want["id"] == 0].max() == 0
     r.close()
+
+
+@pytest.mark.parametrize("name", ["scene", "scene2", "synthetic"])
+def test_table_loops_and_pruning_are_exact(name, scenes_dir):
+    """Forced table loops (threshold 2) with bounding-ball pruning and hoisted short
+    segments vs fully unrolled code: identical distance, id and pixels."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    scene = (lb.Scene.from_string(scenegen.synthetic_scene_text()) if name == "synthetic"
+             else lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol")))
+    w, h = (192, 108) if name == "synthetic" else (640, 360)
+    a = _render(lb, scene, w, h, options=lb.Options.default(loop_threshold=2, prune_bounds=1))
+    b = _render(lb, scene, w, h, options=lb.Options.default(loop_threshold=2, prune_bounds=0))
+    for k in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+    if name != "synthetic":
+        _check(a, ol.port_render(scene, w, h))

@@ -65,13 +65,18 @@ def _scene(lb, name, scenes_dir):
 
 
 @pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
-def test_generated_sdf_equals_oracle_on_cpu(name, scenes_dir, tmp_path):
-    """Each primitive and smooth union as the lowering emits it == sdf.h / float.h."""
+@pytest.mark.parametrize("loops", [0, 2])
+def test_generated_sdf_equals_oracle_on_cpu(name, loops, scenes_dir, tmp_path):
+    """Each primitive and smooth union as the lowering emits it == sdf.h / float.h.
+    loops=2 forces table loops (with bounding-ball pruning and hoisted short
+    segments) onto the small scenes too."""
     import loltracer_b200 as lb
 
     scene = _scene(lb, name, scenes_dir)
-    src = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=2))
-    L = cpu_sdf(tmp_path, src, name)
+    src = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=2, loop_threshold=loops))
+    if loops == 2 and name in ("scene", "scene2"):
+        assert "cannot win" in src  # scene: 2 spheres, scene2: 3 spheres in a row
+    L = cpu_sdf(tmp_path, src, f"{name}{loops}")
     rng = np.random.default_rng(11)
     n = 3000 if name != "synthetic" else 300
     pts = np.concatenate([rng.uniform(-12, 12, (n, 3)), rng.normal(0, 2, (n, 3)) + [0, 1, -6]]).astype(np.float32)
