@@ -267,6 +267,27 @@ int lolb200_deinterleave_device(const void* gathered_dev, void* frame_dev, int w
 /* Pixels a rank's compact buffer needs (bands padded so every rank is equal). */
 size_t lolb200_shard_pixels(int w, int h, int world, int band_rows);
 
+/* ---- several GPUs driven by ONE process (the reference's main.c is one) -------
+ * One renderer per device; the frame is cut into cyclic 4-row bands, band b on
+ * devices[b % n]; devices[0] ends up with the complete frame.
+ *   LOLB200_GATHER_NCCL: compact shards, ncclSend/ncclRecv in one group over
+ *                        NVLink (ncclCommInitAll), de-interleave on devices[0];
+ *   LOLB200_GATHER_PEER: every device's kernel stores its bands straight into
+ *                        devices[0]'s frame through peer access.
+ * render_host then copies the frame into the caller's surface like
+ * lolb200_render_host does.  Calls of one group must come from one thread at a
+ * time (the frame leader of b200_renderer.c). */
+enum { LOLB200_GATHER_NCCL = 0, LOLB200_GATHER_PEER = 1 };
+typedef struct lolb200_group lolb200_group; /* opaque */
+int lolb200_group_create(const lolb200_scene* s, const lolb200_options* o, const int* devices,
+                         int n_devices, int gather, lolb200_group** out);
+void lolb200_group_destroy(lolb200_group* g);
+int lolb200_group_render_host(lolb200_group* g, const lolb200_camera* cam, int w, int h,
+                              const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes);
+/* Milliseconds (CUDA events on devices[0]) of the last frame: render + gather,
+ * without the copy to the host. */
+double lolb200_group_last_frame_ms(const lolb200_group* g);
+
 /* CUDA-IPC plumbing for the peer-store variant (render fused with its gather):
  * export a 64-byte handle for a device allocation / map a peer's handle. */
 int lolb200_ipc_export(void* dev_ptr, uint8_t handle[64]);

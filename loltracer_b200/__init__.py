@@ -10,6 +10,7 @@ calls, it raises.
 from .api import (  # noqa: F401
     Aux,
     Camera,
+    Group,
     LolB200Error,
     Options,
     PixFmt,

@@ -149,6 +149,11 @@ def lib() -> C.CDLL:
         "lolb200_read_counters": (i32, [vp, C.POINTER(C.c_uint64 * 8)]),
         "lolb200_deinterleave_device": (i32, [vp, vp, i32, i32, i32, i32, sz, sz, vp]),
         "lolb200_shard_pixels": (sz, [i32, i32, i32, i32]),
+        "lolb200_group_create": (i32, [C.POINTER(SceneStruct), C.POINTER(Options), C.POINTER(i32), i32, i32,
+                                        C.POINTER(vp)]),
+        "lolb200_group_destroy": (None, [vp]),
+        "lolb200_group_render_host": (i32, [vp, C.POINTER(Camera), i32, i32, C.POINTER(PixFmt), vp, sz]),
+        "lolb200_group_last_frame_ms": (C.c_double, [vp]),
         "lolb200_ipc_export": (i32, [vp, C.POINTER(C.c_uint8 * 64)]),
         "lolb200_ipc_open": (i32, [C.POINTER(C.c_uint8 * 64), C.POINTER(vp)]),
         "lolb200_ipc_close": (i32, [vp]),
@@ -327,3 +332,30 @@ class Renderer:
         names = ("primary_evals", "normal_evals", "shadow_evals", "pixels", "hit_pixels",
                  "shadow_rays", "shadow_rays_culled")
         return dict(zip(names, (int(x) for x in out)))
+
+
+class Group:
+    """Several GPUs driven by one process (what b200_renderer.c --gpus N uses)."""
+
+    GATHER = {"nccl": 0, "peer": 1}
+
+    def __init__(self, scene: Scene, n_devices: int, gather: str = "nccl",
+                 options: Optional[Options] = None, devices: Optional[Sequence[int]] = None):
+        self._h = C.c_void_p()
+        devs = (C.c_int * n_devices)(*(devices or range(n_devices)))
+        _check(lib().lolb200_group_create(scene._ptr, C.byref(options) if options else None, devs,
+                                          n_devices, self.GATHER[gather], C.byref(self._h)))
+
+    def render_host(self, pixels_ptr: int, w: int, h: int, camera: Optional[Camera] = None,
+                    pitch_bytes: Optional[int] = None, fmt: Optional[PixFmt] = None) -> float:
+        _check(lib().lolb200_group_render_host(self._h, C.byref(camera) if camera else None, w, h,
+                                               C.byref(fmt) if fmt else None, pixels_ptr,
+                                               pitch_bytes or w * 4))
+        return float(lib().lolb200_group_last_frame_ms(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.lolb200_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close

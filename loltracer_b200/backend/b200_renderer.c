@@ -33,9 +33,12 @@
 #include "scene_translate.h"
 
 struct b200_state {
-	lolb200_renderer* renderer;
+	lolb200_renderer* renderer; /* one GPU */
+	lolb200_group* group;       /* --gpus N > 1: all of them, driven by the frame leader */
 	lolb200_options options;
 	int device;
+	int gpus;
+	int gather;
 	int verbose;
 };
 
@@ -72,6 +75,10 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 			st->options.variant = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc)
 			st->device = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--gpus") && i + 1 < argc)
+			st->gpus = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--gather") && i + 1 < argc)
+			st->gather = !strcmp(argv[++i], "peer") ? LOLB200_GATHER_PEER : LOLB200_GATHER_NCCL;
 		else if (!strcmp(argv[i], "--dump-cuda") && i + 1 < argc)
 			dump_cuda = argv[++i];
 		else if (!strcmp(argv[i], "--dump-cubin") && i + 1 < argc)
@@ -90,6 +97,19 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 	/* Materials, lights, objects and fov never change after the parse, so they
 	 * are baked into the kernel here; the camera is re-read every frame. */
 	flat = lolb200_scene_from_reference(data->scene);
+	if (st->gpus > 1) {
+		/* the image is sharded in cyclic 4-row bands over GPUs device..device+N-1
+		 * and gathered on the first one over NVLink */
+		int devices[64];
+		if (st->gpus > 64)
+			st->gpus = 64;
+		for (int i = 0; i < st->gpus; i++)
+			devices[i] = st->device + i;
+		if (lolb200_group_create(flat, &st->options, devices, st->gpus, st->gather, &st->group) !=
+		    LOLB200_OK)
+			b200_die("render_prepare");
+	}
+	/* also built with --gpus N: its source and image are what -j dumps */
 	if (lolb200_renderer_create(flat, &st->options, st->device, &st->renderer) != LOLB200_OK)
 		b200_die("render_prepare");
 	lolb200_scene_free(flat);
@@ -116,6 +136,7 @@ void render_destroy(struct render_data* data) {
 	struct b200_state* st = data->private;
 	if (!st)
 		return;
+	lolb200_group_destroy(st->group);
 	lolb200_renderer_destroy(st->renderer);
 	free(st);
 	data->private = NULL;
@@ -145,8 +166,12 @@ static void b200_render_frame(struct render_data* data) {
 	fmt.amask = f->Amask;
 	lolb200__camera_out(&data->scene->camera, &cam); /* main.c:180 moves it every frame */
 
-	if (lolb200_render_host(st->renderer, &cam, surf->w, surf->h, &fmt, surf->pixels,
-	                        (size_t)surf->pitch) != LOLB200_OK)
+	if (st->group) {
+		if (lolb200_group_render_host(st->group, &cam, surf->w, surf->h, &fmt, surf->pixels,
+		                              (size_t)surf->pitch) != LOLB200_OK)
+			b200_die("render_thread");
+	} else if (lolb200_render_host(st->renderer, &cam, surf->w, surf->h, &fmt, surf->pixels,
+	                               (size_t)surf->pitch) != LOLB200_OK)
 		b200_die("render_thread");
 }
 

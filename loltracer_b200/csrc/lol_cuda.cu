@@ -14,6 +14,8 @@
  * LOLB200_ENODEVICE / LOLB200_ECUDA when the GPU is not usable.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <nvrtc.h>
 
 #include <cstdio>
@@ -678,3 +680,275 @@ extern "C" double lolb200_measure_fp32_peak(int device, int iters, double* ms_ou
 	const double flop = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
 	return flop / (best * 1e-3) / 1e12;
 }
+
+/* ------------------------------------------- several GPUs, one host process -- */
+
+namespace {
+
+/* NCCL is bound at run time: a process that already carries an NCCL (PyTorch
+ * bundles one under the same soname) keeps using that copy, and the library
+ * still loads on a box without NCCL as long as nobody asks for this gather. */
+struct NcclApi {
+	void* lib = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	bool load() {
+		if (lib)
+			return true;
+		lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib)
+			lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib)
+			return false;
+#define LOL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name))
+		LOL_SYM(CommInitAll, "ncclCommInitAll");
+		LOL_SYM(CommDestroy, "ncclCommDestroy");
+		LOL_SYM(GroupStart, "ncclGroupStart");
+		LOL_SYM(GroupEnd, "ncclGroupEnd");
+		LOL_SYM(Send, "ncclSend");
+		LOL_SYM(Recv, "ncclRecv");
+		LOL_SYM(GetErrorString, "ncclGetErrorString");
+#undef LOL_SYM
+		return CommInitAll && CommDestroy && GroupStart && GroupEnd && Send && Recv && GetErrorString;
+	}
+};
+
+NcclApi g_nccl;
+
+} // namespace
+
+struct lolb200_group {
+	int n = 0;
+	int gather = LOLB200_GATHER_NCCL;
+	std::vector<int> devices;
+	std::vector<lolb200_renderer*> renderers;
+	std::vector<cudaStream_t> streams;
+	std::vector<cudaEvent_t> done;       /* rank i finished its kernel */
+	std::vector<ncclComm_t> comms;
+	std::vector<lol_u32*> shard;         /* compact shard of rank i (rank 0: gathered[0]) */
+	lol_u32* gathered = nullptr;         /* devices[0]: n shards back to back */
+	lol_u32* frame = nullptr;            /* devices[0]: the complete frame */
+	size_t shard_px = 0, frame_px = 0;
+	int w = 0, h = 0;
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	double last_ms = 0.0;
+	void* registered = nullptr;
+	size_t registered_bytes = 0;
+};
+
+#define NCCL_TRY(expr)                                                                   \
+	do {                                                                                 \
+		ncclResult_t r_ = (expr);                                                        \
+		if (r_ != ncclSuccess) {                                                         \
+			lolb200_set_error("%s failed: %s", #expr, g_nccl.GetErrorString(r_));        \
+			return LOLB200_ECUDA;                                                        \
+		}                                                                                \
+	} while (0)
+
+extern "C" void lolb200_group_destroy(lolb200_group* g) {
+	if (!g)
+		return;
+	for (int i = 0; i < g->n; ++i) {
+		if (i < (int)g->devices.size())
+			cudaSetDevice(g->devices[i]);
+		if (i < (int)g->streams.size() && g->streams[i]) {
+			cudaStreamSynchronize(g->streams[i]);
+			cudaStreamDestroy(g->streams[i]);
+		}
+		if (i < (int)g->done.size() && g->done[i])
+			cudaEventDestroy(g->done[i]);
+		if (i < (int)g->comms.size() && g->comms[i])
+			g_nccl.CommDestroy(g->comms[i]);
+		if (i > 0 && i < (int)g->shard.size())
+			cudaFree(g->shard[i]);
+		if (i < (int)g->renderers.size())
+			lolb200_renderer_destroy(g->renderers[i]);
+	}
+	if (!g->devices.empty()) {
+		cudaSetDevice(g->devices[0]);
+		if (g->registered)
+			cudaHostUnregister(g->registered);
+		cudaFree(g->gathered);
+		cudaFree(g->frame);
+		if (g->t0)
+			cudaEventDestroy(g->t0);
+		if (g->t1)
+			cudaEventDestroy(g->t1);
+	}
+	delete g;
+}
+
+extern "C" int lolb200_group_create(const lolb200_scene* s, const lolb200_options* o,
+                                    const int* devices, int n, int gather, lolb200_group** out) {
+	if (!s || !out || n < 1 || n > 64 || (gather != LOLB200_GATHER_NCCL && gather != LOLB200_GATHER_PEER)) {
+		lolb200_set_error("lolb200_group_create: bad argument");
+		return LOLB200_EINVAL;
+	}
+	*out = nullptr;
+	lolb200_group* g = new lolb200_group();
+	g->n = n;
+	g->gather = gather;
+	for (int i = 0; i < n; ++i)
+		g->devices.push_back(devices ? devices[i] : i);
+	g->streams.assign(n, nullptr);
+	g->done.assign(n, nullptr);
+	g->comms.assign(n, nullptr);
+	g->shard.assign(n, nullptr);
+#define GROUP_FAIL(rc_)              \
+	do {                             \
+		lolb200_group_destroy(g);    \
+		return (rc_);                \
+	} while (0)
+	for (int i = 0; i < n; ++i) {
+		lolb200_renderer* r = nullptr;
+		int rc = lolb200_renderer_create(s, o, g->devices[i], &r);
+		if (rc != LOLB200_OK)
+			GROUP_FAIL(rc);
+		g->renderers.push_back(r);
+		if (cudaSetDevice(g->devices[i]) != cudaSuccess ||
+		    cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&g->done[i], cudaEventDisableTiming) != cudaSuccess) {
+			lolb200_set_error("lolb200_group_create: stream setup failed on device %d", g->devices[i]);
+			GROUP_FAIL(LOLB200_ECUDA);
+		}
+	}
+	cudaSetDevice(g->devices[0]);
+	cudaEventCreate(&g->t0);
+	cudaEventCreate(&g->t1);
+	if (n > 1 && gather == LOLB200_GATHER_NCCL) {
+		if (!g_nccl.load()) {
+			lolb200_set_error("cannot load libnccl.so.2: %s", dlerror());
+			GROUP_FAIL(LOLB200_ECUDA);
+		}
+		ncclResult_t nr = g_nccl.CommInitAll(g->comms.data(), n, g->devices.data());
+		if (nr != ncclSuccess) {
+			lolb200_set_error("ncclCommInitAll failed: %s", g_nccl.GetErrorString(nr));
+			GROUP_FAIL(LOLB200_ECUDA);
+		}
+	}
+	if (n > 1 && gather == LOLB200_GATHER_PEER) {
+		for (int i = 1; i < n; ++i) {
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, g->devices[i], g->devices[0]);
+			if (!can) {
+				lolb200_set_error("device %d cannot store into device %d (no peer access)",
+				                  g->devices[i], g->devices[0]);
+				GROUP_FAIL(LOLB200_ECUDA);
+			}
+			cudaSetDevice(g->devices[i]);
+			cudaError_t e = cudaDeviceEnablePeerAccess(g->devices[0], 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+				lolb200_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+				GROUP_FAIL(LOLB200_ECUDA);
+			}
+			cudaGetLastError();
+		}
+	}
+#undef GROUP_FAIL
+	*out = g;
+	return LOLB200_OK;
+}
+
+static int group_resize(lolb200_group* g, int w, int h) {
+	if (g->w == w && g->h == h)
+		return LOLB200_OK;
+	const size_t shard_px = lolb200_shard_pixels(w, h, g->n, 0);
+	cudaSetDevice(g->devices[0]);
+	cudaFree(g->gathered);
+	cudaFree(g->frame);
+	g->gathered = g->frame = nullptr;
+	CUDA_TRY(cudaMalloc(&g->frame, (size_t)w * h * sizeof(lol_u32)));
+	if (g->gather == LOLB200_GATHER_NCCL && g->n > 1) {
+		CUDA_TRY(cudaMalloc(&g->gathered, shard_px * g->n * sizeof(lol_u32)));
+		g->shard[0] = g->gathered;
+		for (int i = 1; i < g->n; ++i) {
+			cudaSetDevice(g->devices[i]);
+			cudaFree(g->shard[i]);
+			g->shard[i] = nullptr;
+			CUDA_TRY(cudaMalloc(&g->shard[i], shard_px * sizeof(lol_u32)));
+		}
+	}
+	g->shard_px = shard_px;
+	g->w = w;
+	g->h = h;
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera* cam, int w, int h,
+                                         const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes) {
+	if (!g || !pixels || w <= 0 || h <= 0 || pitch_bytes < (size_t)w * 4) {
+		lolb200_set_error("lolb200_group_render_host: bad argument");
+		return LOLB200_EINVAL;
+	}
+	if (g->n == 1)
+		return lolb200_render_host(g->renderers[0], cam, w, h, fmt, pixels, pitch_bytes);
+	int rc = group_resize(g, w, h);
+	if (rc != LOLB200_OK)
+		return rc;
+	cudaSetDevice(g->devices[0]);
+	const size_t bytes = pitch_bytes * (size_t)h;
+	if (g->registered != pixels || g->registered_bytes != bytes) {
+		if (g->registered)
+			cudaHostUnregister(g->registered);
+		g->registered = nullptr;
+		if (cudaHostRegister(pixels, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+			g->registered = pixels;
+			g->registered_bytes = bytes;
+		} else {
+			cudaGetLastError();
+		}
+	}
+	CUDA_TRY(cudaEventRecord(g->t0, g->streams[0]));
+	for (int i = 0; i < g->n; ++i) {
+		lolb200_shard sh = {i, g->n, 0, g->gather == LOLB200_GATHER_PEER ? 1 : 0};
+		if (i > 0) {
+			/* rank i starts after devices[0]'s t0 so the timing brackets all ranks */
+			cudaSetDevice(g->devices[i]);
+			CUDA_TRY(cudaStreamWaitEvent(g->streams[i], g->t0, 0));
+		}
+		void* dst = g->gather == LOLB200_GATHER_PEER ? (void*)g->frame : (void*)g->shard[i];
+		rc = lolb200_render_device(g->renderers[i], cam, w, h, fmt, &sh, dst, (size_t)w, nullptr,
+		                           g->streams[i]);
+		if (rc != LOLB200_OK)
+			return rc;
+	}
+	if (g->gather == LOLB200_GATHER_NCCL) {
+		NCCL_TRY(g_nccl.GroupStart());
+		for (int i = 1; i < g->n; ++i) {
+			NCCL_TRY(g_nccl.Send(g->shard[i], g->shard_px, ncclInt32, 0, g->comms[i], g->streams[i]));
+			NCCL_TRY(g_nccl.Recv(g->gathered + (size_t)i * g->shard_px, g->shard_px, ncclInt32, i,
+			                     g->comms[0], g->streams[0]));
+		}
+		NCCL_TRY(g_nccl.GroupEnd());
+		cudaSetDevice(g->devices[0]);
+		rc = lolb200_deinterleave_device(g->gathered, g->frame, w, h, g->n, 0, g->shard_px, (size_t)w,
+		                                 g->streams[0]);
+		if (rc != LOLB200_OK)
+			return rc;
+	} else {
+		/* peer stores: the frame is complete once every rank's kernel has retired */
+		for (int i = 1; i < g->n; ++i) {
+			cudaSetDevice(g->devices[i]);
+			CUDA_TRY(cudaEventRecord(g->done[i], g->streams[i]));
+		}
+		cudaSetDevice(g->devices[0]);
+		for (int i = 1; i < g->n; ++i)
+			CUDA_TRY(cudaStreamWaitEvent(g->streams[0], g->done[i], 0));
+	}
+	cudaSetDevice(g->devices[0]);
+	CUDA_TRY(cudaEventRecord(g->t1, g->streams[0]));
+	CUDA_TRY(cudaMemcpy2DAsync(pixels, pitch_bytes, g->frame, (size_t)w * 4, (size_t)w * 4, (size_t)h,
+	                           cudaMemcpyDeviceToHost, g->streams[0]));
+	CUDA_TRY(cudaStreamSynchronize(g->streams[0]));
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, g->t0, g->t1) == cudaSuccess)
+		g->last_ms = ms;
+	return LOLB200_OK;
+}
+
+extern "C" double lolb200_group_last_frame_ms(const lolb200_group* g) { return g ? g->last_ms : 0.0; }

@@ -46,3 +46,48 @@ def test_backend_dumps_generated_code(scenes_dir, tmp_path):
     assert out.returncode == 0, out.stderr
     assert "lol_sdf" in (tmp_path / "lol-b200-kernel.cu").read_text()
     assert (tmp_path / "lol-b200-kernel.cubin").read_bytes()[:4] == b"\x7fELF"
+
+
+@pytest.mark.parametrize("gather", ["nccl", "peer"])
+def test_backend_on_all_gpus_of_the_box(gather, scenes_dir, tmp_path):
+    """--gpus N: one host process drives every GPU; same frame as one GPU.  Needs >= 2 GPUs
+    (gpurun --gpus 2); on a single-GPU box it is skipped."""
+    import loltracer_b200 as lb
+
+    n = lb.device_count()
+    if n < 2:
+        pytest.skip("one GPU on this box")
+    if not os.path.exists(HOST):
+        pytest.skip("headless host not built")
+    w, h = 1283, 721
+    path = os.path.join(scenes_dir, "scene4.lol")
+    frames = []
+    for gpus in (1, n):
+        raw = tmp_path / f"frame{gpus}.bin"
+        out = subprocess.run([HOST, "4", path, "--size", f"{w}x{h}", "--frames", "3", "--gpus", str(gpus),
+                              "--gather", gather, "--raw", str(raw)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr
+        frames.append(np.fromfile(raw, np.uint32))
+    assert np.array_equal(frames[0], frames[1])
+
+
+def test_group_api_matches_single_gpu(scenes_dir):
+    import loltracer_b200 as lb
+
+    n = lb.device_count()
+    if n < 2:
+        pytest.skip("one GPU on this box")
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    w, h = 1000, 563
+    one = np.zeros((h, w), np.uint32)
+    r = lb.Renderer(scene)
+    r.render_host(one.ctypes.data, w, h)
+    for gather in ("nccl", "peer"):
+        g = lb.Group(scene, n, gather)
+        got = np.zeros((h, w), np.uint32)
+        for _ in range(2):
+            ms = g.render_host(got.ctypes.data, w, h)
+        assert np.array_equal(got, one), gather
+        assert ms > 0
+        g.close()
+    r.close()
