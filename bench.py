@@ -39,8 +39,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="scene4")
-    ap.add_argument("--size", default="3840x2160")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"])
+    ap.add_argument("--size", default=None, help="default 3840x2160 (frame) / 7680x4320 (orbit)")
+    ap.add_argument("--gather", default="peer", choices=["nccl", "peer"])
+    ap.add_argument("--workload", default="frame", choices=["frame", "orbit"],
+                    help="frame: one frame per step, sharded by bands over the GPUs (configs C1-C4); "
+                         "orbit: one step = 64 camera-orbit frames, whole frames dealt to the GPUs (C5)")
+    ap.add_argument("--orbit-frames", type=int, default=64)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -114,7 +118,7 @@ class ClockSampler:
 # ------------------------------------------------------------ CPU baseline --
 
 
-def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False):
+def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False, want_totals=True):
     """The reference's naive renderer (oracle/_ref, built from its own sources) -- or the
     oracle port when that library did not travel -- on every `ystride`-th scanline of the
     w x h frame, all host threads.  Returns (best_ms, rays, kind, cores, totals)."""
@@ -125,7 +129,8 @@ def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False):
     rows = (h + ystride - 1) // ystride
     rays = rows * w
     scene = load_scene(lb, scene_name)
-    totals = ol.port_render(scene, w, h, ystride=ystride)["totals"]  # also warms the threads up
+    # evaluation counts of the sample (oracle port; also warms the threads up)
+    totals = ol.port_render(scene, w, h, ystride=ystride)["totals"] if want_totals else None
     best = None
     if ol.have_ref() and not force_port and scene_name != "synthetic-port":
         kind = "reference"
@@ -163,14 +168,15 @@ def run_reference(args, w, h):
     while stride < 64 and per_row_ms * ((h + stride - 1) // stride) > budget_ms:
         stride *= 2
     for _ in range(args.warmup):
-        cpu_sample(args.scene, w, h, stride)
+        cpu_sample(args.scene, w, h, stride, want_totals=False)
     t_total, rays = 0.0, 0
     for _ in range(args.steps):
-        ms, rays, kind, cores, _ = cpu_sample(args.scene, w, h, stride)
+        ms, rays, kind, cores, _ = cpu_sample(args.scene, w, h, stride, want_totals=False)
         t_total += ms
     ms_per_step = t_total / args.steps
     value = rays / (ms_per_step * 1e-3) / 1e6
-    sample = (f"every {stride}th scanline of the {w}x{h} frame ({rays} primary rays per step), "
+    sample = (f"{'every scanline' if stride == 1 else f'every {stride}th scanline'} of the {w}x{h} frame "
+              f"({rays} primary rays per step), "
               f"{'naive_renderer.c compiled unmodified' if kind == 'reference' else 'oracle port'}, "
               f"{cores} threads pulling scanlines from one atomic counter")
     print(json.dumps({
@@ -196,11 +202,87 @@ def flops_model(f_sdf, n_lights, pixels, primary, normal, shadow, shaded, rays_m
             95 * rays_marched + 20 * rays_culled + 50 * pixels)
 
 
+
+def run_orbit(args, lb, torch, dist, scene, renderer, world, rank, local_rank, dev, w, h):
+    """Config C5, throughput mode: one step = F camera-orbit frames of the scene; whole
+    frames are dealt to the ranks (frame k -> rank k % N) and stay in that rank's HBM: no
+    data-path collective.  value = F*W*H rays / step time (max over ranks)."""
+    import time as _time
+    from loltracer_b200 import scenegen
+
+    F, K, W = args.orbit_frames, args.steps, max(args.warmup, 3)
+    cams = [scenegen.orbit_camera(scene.camera, k, F) for k in range(F)]
+    mine = [k for k in range(F) if k % world == rank]
+    stream = torch.cuda.current_stream().cuda_stream
+    frames = torch.zeros((max(1, len(mine)), h, w), dtype=torch.int32, device=dev)  # all resident
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        for i, k in enumerate(mine):
+            renderer.render_device(frames[i].data_ptr(), w, h, camera=cams[k], stream=stream)
+
+    for _ in range(W):
+        step()
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+        sync_all()
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+
+    host = torch.empty((h, w), dtype=torch.int32).pin_memory()
+    for k in mine[:2]:
+        renderer.render_host(host.data_ptr(), w, h, camera=cams[k])
+    sync_all()
+    t0 = _time.perf_counter()
+    for _ in range(max(1, K // 4)):
+        for k in mine:
+            renderer.render_host(host.data_ptr(), w, h, camera=cams[k])
+    sync_all()
+    e2e_ms = (_time.perf_counter() - t0) / max(1, K // 4) * 1e3
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        ms_per_step = total_ms / K
+        rays = F * w * h
+        print(json.dumps({
+            "metric": METRIC, "value": rays / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "ms_per_frame": ms_per_step / F,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{F}-frame camera orbit of {args.scene}.lol at {w}x{h} (BASELINE config C5), "
+                                   f"whole frames dealt to ranks, frames left in each rank's HBM",
+                       "arith": args.arith, "variant": args.variant,
+                       "l2": "256 MB write between timed steps (untimed)", "kernel": renderer.kernel_info()},
+            "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms / F,
+                    "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": rays * 4},
+            "gpu_launches": K * len(mine),
+            "clocks": clocks.summary(),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
 # ------------------------------------------------------------------- main --
 
 
 def main():
     args = parse_args()
+    if args.size is None:
+        args.size = "7680x4320" if args.workload == "orbit" else "3840x2160"
     w, h = (int(x) for x in args.size.lower().split("x"))
     if args.impl == "reference":
         return run_reference(args, w, h)
@@ -233,6 +315,8 @@ def main():
     renderer = lb.Renderer(scene, opt, device=local_rank)
     stream = torch.cuda.current_stream().cuda_stream
     K, W = args.steps, args.warmup
+    if args.workload == "orbit":
+        return run_orbit(args, lb, torch, dist, scene, renderer, world, rank, local_rank, dev, w, h)
 
     shard_px = lb.shard_pixels(w, h, world)
     frame = torch.zeros((h, w), dtype=torch.int32, device=dev) if rank == 0 else None
@@ -337,6 +421,15 @@ def main():
     ms_per_step = total_ms / K
     value = w * h / (ms_per_step * 1e-3) / 1e6
 
+    # ---- the sharded frame must be the single-GPU frame, bit for bit ----
+    verified = None
+    if world > 1 and rank == 0:
+        check = torch.zeros((h, w), dtype=torch.int32, device=dev)
+        renderer.render_device(check.data_ptr(), w, h, stream=stream)
+        torch.cuda.synchronize()
+        verified = bool(torch.equal(check, frame))
+        del check
+
     # ---- e2e: host buffers, D2H inside the timed region ----
     host = torch.empty((h, w), dtype=torch.int32).pin_memory() if rank == 0 else None
 
@@ -417,6 +510,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                 "h2d_bytes_per_step": 192, "d2h_bytes_per_step": w * h * 4},
         "gpu_launches": n_launches,
+        "sharded_frame_equals_single_gpu": verified,
         "roofline": roofline,
         "clocks": clocks.summary(),
         "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
@@ -425,8 +519,9 @@ def main():
     }
 
     if world == 1 and not args.no_cpu_baseline:
-        # ~20 core-seconds on scene4: every 4th scanline of the same frame
-        stride = 4 if args.scene != "synthetic" else 64
+        # ~20 core-seconds on scene4: every 4th scanline of the same frame; the
+        # 1024-primitive scene costs ~1000x more per ray, so only a few scanlines
+        stride = 4 if args.scene != "synthetic" else max(4, h // 3)
         ms, rays, kind, cores, totals = cpu_sample(args.scene, w, h, stride)
         cpu_value = rays / (ms * 1e-3) / 1e6
         out["cpu_baseline"] = {
