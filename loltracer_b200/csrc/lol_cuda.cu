@@ -107,8 +107,24 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 	if (log)
 		*log = nullptr;
 
+	/* LOLB200_DUMP_DIR=<dir>: keep the generated program as <dir>/lol-<hash>.cu and
+	 * compile it under that name, so -lineinfo points at a file a profiler can
+	 * import (ncu --import-source on).  The analogue of the JIT's perf map. */
+	std::string prog_name = "lol_scene.cu";
+	if (const char* dir = getenv("LOLB200_DUMP_DIR")) {
+		unsigned long long hsh = 1469598103934665603ull;
+		for (const char* c = src; *c; ++c)
+			hsh = (hsh ^ (unsigned char)*c) * 1099511628211ull;
+		char path[4096];
+		snprintf(path, sizeof path, "%s/lol-%016llx.cu", dir, hsh);
+		if (FILE* f = fopen(path, "w")) {
+			fputs(src, f);
+			fclose(f);
+			prog_name = path;
+		}
+	}
 	nvrtcProgram prog;
-	nvrtcResult r = nvrtcCreateProgram(&prog, src, "lol_scene.cu", 0, nullptr, nullptr);
+	nvrtcResult r = nvrtcCreateProgram(&prog, src, prog_name.c_str(), 0, nullptr, nullptr);
 	if (r != NVRTC_SUCCESS) {
 		lolb200_set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
 		return LOLB200_ECOMPILE;
