@@ -155,8 +155,10 @@ typedef struct lolb200_options {
 	                            returned value is then exactly 0)               */
 	int32_t counters;        /* 1: kernel also accumulates per-phase SDF
 	                            evaluation counts (instrumented build)          */
-	int32_t variant;         /* kernel structure: 0 = default for this build,
-	                            1 = phase-sequential, 2 = megaloop + lane refill */
+	int32_t variant;         /* kernel structure: 0 = chosen per scene,
+	                            1 = phase-sequential, 2 = megaloop + lane refill,
+	                            3 = two rays per thread in packed FP32 registers
+	                                (FADD2/FMUL2/FFMA2; needs the guarded forms) */
 	int32_t loop_threshold;  /* top-level runs of >= this many same-shape
 	                            objects become a loop over __constant__ tables;
 	                            0 = default (16)                                */
@@ -170,7 +172,16 @@ typedef struct lolb200_options {
 	int32_t prune_bounds;    /* 1: inside table loops an object is skipped when a
 	                            conservative bounding ball proves it cannot
 	                            beat the running minimum (exact)     */
-	int32_t reserved[7];
+	int32_t block_threads;   /* tuning: threads per CTA (multiple of 32);
+	                            0 = the variant's default                       */
+	int32_t min_blocks;      /* tuning: __launch_bounds__ second argument (caps
+	                            registers so that this many CTAs fit on an SM);
+	                            0 = the variant's default                       */
+	int32_t roll_phases;     /* tuning, variant 3: 1 = the normal taps and the
+	                            lights are loops around ONE copy of the distance
+	                            code each (instruction-cache footprint), 0 =
+	                            unrolled; -1... not used; default 1             */
+	int32_t reserved[4];
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

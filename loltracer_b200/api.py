@@ -72,7 +72,8 @@ class Options(C.Structure):
                 ("cull_backfacing", C.c_int32), ("shadow_early_out", C.c_int32),
                 ("counters", C.c_int32), ("variant", C.c_int32), ("loop_threshold", C.c_int32),
                 ("guarded_fastpath", C.c_int32), ("prune_bounds", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("block_threads", C.c_int32), ("min_blocks", C.c_int32), ("roll_phases", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
     @classmethod
     def default(cls, **kw) -> "Options":

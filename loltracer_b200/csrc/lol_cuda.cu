@@ -73,6 +73,7 @@ struct lolb200_renderer {
 	int blocks_per_sm = 1;
 	int regs = 0, smem = 0, local = 0, max_threads = 0;
 	int variant = 1;
+	int threads = LOLB200_KERNEL_THREADS; /* CTA size the program was generated for */
 	size_t dyn_smem = 0; /* variant 2: warp-private queues */
 	lol_u32* counter = nullptr; /* device: [0] next chunk, [1] finished CTAs */
 	lol_u64* stats = nullptr;   /* device: 8 accumulators (options.counters) */
@@ -292,10 +293,13 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 		/* the lowering states what it generated */
 		const char* v = strstr(r->source.c_str(), "#define LOL_VARIANT ");
 		r->variant = v ? atoi(v + strlen("#define LOL_VARIANT ")) : 1;
+		const char* th = strstr(r->source.c_str(), "#define LOL_THREADS ");
+		if (th)
+			r->threads = atoi(th + strlen("#define LOL_THREADS "));
 		const char* sm = strstr(r->source.c_str(), "#define LOL_SMEM_PER_WARP ");
 		if (r->variant == 2 && sm) {
 			r->dyn_smem = (size_t)atol(sm + strlen("#define LOL_SMEM_PER_WARP ")) *
-			              (LOLB200_KERNEL_THREADS / 32);
+			              (r->threads / 32);
 			CREATE_TRY(cudaFuncSetAttribute((const void*)r->kernel,
 			                                cudaFuncAttributeMaxDynamicSharedMemorySize,
 			                                (int)r->dyn_smem));
@@ -309,7 +313,7 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	r->max_threads = fa.maxThreadsPerBlock;
 	int occ = 0;
 	CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)r->kernel,
-	                                                         LOLB200_KERNEL_THREADS, r->dyn_smem));
+	                                                         r->threads, r->dyn_smem));
 	r->blocks_per_sm = occ > 0 ? occ : 1;
 	/* one (next chunk, finished CTAs) pair per slab, so slab launches may overlap */
 	CREATE_TRY(cudaMalloc(&r->counter, 2 * LOL_MAX_SLABS * sizeof(lol_u32)));
@@ -371,13 +375,15 @@ extern "C" size_t lolb200_shard_pixels(int w, int h, int world, int band_rows) {
 /* Work chunks are chunk_w x 4 pixels.  Wide chunks mean fewer atomics on the
  * one counter; narrow ones keep every warp busy when a shard is small. */
 static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands) {
-	const size_t warps = (size_t)r->sm_count * r->blocks_per_sm * (LOLB200_KERNEL_THREADS / 32);
-	for (lol_u32 cw = r->variant == 2 ? 32 : 64; cw > 8; cw >>= 1) {
+	const size_t warps = (size_t)r->sm_count * r->blocks_per_sm * (r->threads / 32);
+	/* variant 3: a warp step covers 16 x 4 pixels (two per lane) */
+	const lol_u32 min_w = r->variant == 3 ? 16 : 8;
+	for (lol_u32 cw = r->variant == 2 ? 32 : 64; cw > min_w; cw >>= 1) {
 		size_t chunks = (((size_t)w + cw - 1) / cw) * local_bands;
 		if (chunks >= 16 * warps)
 			return cw;
 	}
-	return 8;
+	return min_w;
 }
 
 /* One launch over local bands [band_begin, band_begin + band_count) of the
@@ -455,12 +461,11 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 	DeviceGuard g(r->device);
 	const size_t warps_needed = P.n_chunks;
 	size_t grid = (size_t)r->sm_count * r->blocks_per_sm;
-	const size_t grid_needed = (warps_needed + LOLB200_KERNEL_THREADS / 32 - 1) /
-	                           (LOLB200_KERNEL_THREADS / 32);
+	const size_t grid_needed = (warps_needed + r->threads / 32 - 1) / (r->threads / 32);
 	if (grid > grid_needed)
 		grid = grid_needed;
 	void* args[] = {&P};
-	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3(LOLB200_KERNEL_THREADS),
+	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3((unsigned)r->threads),
 	                          args, r->dyn_smem, (cudaStream_t)stream));
 	return LOLB200_OK;
 }

@@ -92,6 +92,7 @@ struct cgen {
 	int in_loop;  /* 1: constants are c[j], gathered into row[] */
 	int fast;     /* 1: guarded fast forms (lol_sqrt_fast, lol_smin_c) */
 	int div_ok;   /* 1: every smoothness passed the constant-division proof */
+	int two;      /* 1: two rays per evaluation, packed FP32 (lol_f2, variant 3) */
 	float* row;
 	size_t nrow, caprow;
 	const char* indent;
@@ -139,6 +140,7 @@ static void coord_minus(struct cgen* g, const char* x, float c) {
  * Returns N.  Children of a smooth union see the same (x, y, z). */
 static int emit_node(struct cgen* g, uint32_t idx) {
 	const lolb200_object* o = &g->s->nodes[idx];
+	const char* T = g->two ? "lol_f2" : "float";
 	int me;
 
 	switch (o->type) {
@@ -146,16 +148,20 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 		me = g->tmp++;
 		if (g->fast) {
 			/* same operations; the squared length also feeds the range guard */
-			sb_printf(g->out, "%sconst float qx%d = ", g->indent, me);
+			sb_printf(g->out, "%sconst %s qx%d = ", g->indent, T, me);
 			coord_minus(g, "x", o->point[0]);
 			sb_printf(g->out, ", qy%d = ", me);
 			coord_minus(g, "y", o->point[1]);
 			sb_printf(g->out, ", qz%d = ", me);
 			coord_minus(g, "z", o->point[2]);
-			sb_printf(g->out, ";\n%sconst float s%d = lol_dot(qx%d, qy%d, qz%d, qx%d, qy%d, qz%d);\n",
-			          g->indent, me, me, me, me, me, me, me);
-			sb_printf(g->out, "%slo = fminf(lo, s%d);\n", g->indent, me);
-			sb_printf(g->out, "%sconst float t%d = lol_sqrt_fast(s%d) - ", g->indent, me, me);
+			sb_printf(g->out, ";\n%sconst %s s%d = lol_dot%s(qx%d, qy%d, qz%d, qx%d, qy%d, qz%d);\n",
+			          g->indent, T, me, g->two ? "2" : "", me, me, me, me, me, me);
+			if (g->two)
+				sb_printf(g->out, "%slo = lol_min_halves(lo, s%d);\n", g->indent, me);
+			else
+				sb_printf(g->out, "%slo = fminf(lo, s%d);\n", g->indent, me);
+			sb_printf(g->out, "%sconst %s t%d = lol_sqrt_fast%s(s%d) - ", g->indent, T, me,
+			          g->two ? "2" : "", me);
 			cst(g, o->radius);
 			sb_printf(g->out, ";\n");
 			return me;
@@ -172,6 +178,23 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 		return me;
 	case LOLB200_OBJ_BOX: /* sdRoundBox, sdf.h:18-22 */
 		me = g->tmp++;
+		if (g->two) {
+			/* no two-wide abs/max: the box runs per half on the packed coordinates */
+			sb_printf(g->out, "%sconst lol_f2 t%d = lol_roundbox2(", g->indent, me);
+			coord_minus(g, "x", o->point[0]);
+			sb_printf(g->out, ", ");
+			coord_minus(g, "y", o->point[1]);
+			sb_printf(g->out, ", ");
+			coord_minus(g, "z", o->point[2]);
+			for (int k = 0; k < 3; k++) {
+				sb_printf(g->out, ", ");
+				cst(g, o->point2[k]);
+			}
+			sb_printf(g->out, ", ");
+			cst(g, o->radius);
+			sb_printf(g->out, ");\n");
+			return me;
+		}
 		sb_printf(g->out, "%sconst float t%d = lol_roundbox(fabsf(", g->indent, me);
 		coord_minus(g, "x", o->point[0]);
 		sb_printf(g->out, ") - ");
@@ -190,7 +213,7 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 		return me;
 	case LOLB200_OBJ_PLANE: /* point.y, naive_renderer.c:19-20 */
 		me = g->tmp++;
-		sb_printf(g->out, "%sconst float t%d = ", g->indent, me);
+		sb_printf(g->out, "%sconst %s t%d = ", g->indent, T, me);
 		coord_minus(g, "y", o->point[1]);
 		sb_printf(g->out, ";\n");
 		return me;
@@ -200,13 +223,15 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 		const float rk = 1.0f / o->smoothness;
 		me = g->tmp++;
 		if (g->fast && g->div_ok) {
-			sb_printf(g->out, "%sconst float t%d = lol_smin_c(t%d, t%d, ", g->indent, me, a, b);
+			sb_printf(g->out, "%sconst %s t%d = lol_smin_c%s(t%d, t%d, ", g->indent, T, me,
+			          g->two ? "2" : "", a, b);
 			cst(g, o->smoothness);
 			sb_printf(g->out, ", ");
 			cst(g, rk);
 			sb_printf(g->out, ");\n");
 		} else {
-			sb_printf(g->out, "%sconst float t%d = lol_smin(t%d, t%d, ", g->indent, me, a, b);
+			sb_printf(g->out, "%sconst %s t%d = lol_smin%s(t%d, t%d, ", g->indent, T, me,
+			          g->two ? "2" : "", a, b);
 			cst(g, o->smoothness);
 			cst_skip(g, rk);
 			sb_printf(g->out, ");\n");
@@ -295,9 +320,9 @@ static void bound_row(const lolb200_scene* s, uint32_t idx, float row[4]) {
  * hands the whole evaluation to `fallback` when its one range check fails. */
 static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_scene* s,
                         int loop_threshold, const char* name, const char* attrs, int fast,
-                        int div_ok, const char* fallback, int prune) {
+                        int div_ok, const char* fallback, int prune, int two) {
 	struct sb body = {0}, tables = {0};
-	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok};
+	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok, .two = two};
 	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
 	size_t table_bytes = 0;
 	int run_no = 0;
@@ -314,7 +339,16 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 	sb_printf(&body,
 	          "// sdf (naive_renderer.c:30-44): running strict-< minimum over the top-level\n"
 	          "// objects, ids 1..n in file order, (INF, 0) when nothing is closer.\n");
-	if (packed)
+	if (two)
+		sb_printf(&body,
+		          "// Two rays per call: x, y, z hold ray A in the low and ray B in the high half.\n"
+		          "__device__ %s lol_f2 %s(const lol_f2 x, const lol_f2 y, const lol_f2 z,\n"
+		          "                                         lol_u32& idA, lol_u32& idB) {\n"
+		          "\tfloat bestA = LOL_INF, bestB = LOL_INF;\n\tlol_u32 bidA = 0u, bidB = 0u;\n"
+		          "\t// One range guard per evaluation, over both rays.\n"
+		          "\tfloat lo = LOL_COORD_MAX - lol_max_abs_halves(x, y, z);\n",
+		          attrs, name);
+	else if (packed)
 		sb_printf(&body, "__device__ %s lol_u64 %s(const float x, const float y, const float z) {\n",
 		          attrs, name);
 	else
@@ -322,8 +356,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "__device__ %s float %s(const float x, const float y, const float z,\n"
 		          "                                         lol_u32& id) {\n",
 		          attrs, name);
-	sb_printf(&body, "\tfloat best = LOL_INF;\n\tlol_u32 bid = 0u;\n");
-	if (fast)
+	if (!two)
+		sb_printf(&body, "\tfloat best = LOL_INF;\n\tlol_u32 bid = 0u;\n");
+	if (fast && !two)
 		sb_printf(&body,
 		          "\t// One range guard per evaluation: lo = min(every sqrt argument, 2^60 - max|p|).\n"
 		          "\tfloat lo = LOL_COORD_MAX - fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));\n");
@@ -363,7 +398,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			for (uint32_t k = i; k < j; k++) {
 				struct sb scratch = {0};
 				struct cgen r = {.s = s, .out = (k == i) ? &body : &scratch, .in_loop = 1,
-				                 .indent = "\t\t", .fast = fast, .div_ok = div_ok};
+				                 .indent = "\t\t", .fast = fast, .div_ok = div_ok, .two = two};
 				float ball[4];
 				if (k == i) {
 					sb_printf(&body, "#pragma unroll 1\n\tfor (int i = 0; i < %u; ++i) {\n",
@@ -377,7 +412,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					if (k == i)
 						sb_printf(&body,
 						          "\t\t{ // dist(object, p) >= |p - C| - R >= best: cannot win\n"
-						          "\t\t\tconst float bx = x - ");
+						          "\t\t\tconst %s bx = x - ", two ? "lol_f2" : "float");
 					cst(&r, ball[0]);
 					if (k == i)
 						sb_printf(&body, ", by = y - ");
@@ -386,16 +421,37 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						sb_printf(&body, ", bz = z - ");
 					cst(&r, ball[2]);
 					if (k == i)
-						sb_printf(&body, ";\n\t\t\tconst float u = (best + ");
+						sb_printf(&body, two ? ";\n\t\t\tconst float rr = " : ";\n\t\t\tconst float u = (best + ");
 					cst(&r, ball[3]);
-					if (k == i)
+					if (k == i && two)
+						sb_printf(&body,
+						          ";\n\t\t\tconst float uA = (bestA + rr) * LOL_F(0x3f808312 /*1.004*/);\n"
+						          "\t\t\tconst float uB = (bestB + rr) * LOL_F(0x3f808312 /*1.004*/);\n"
+						          "\t\t\tconst lol_f2 dd = lol_dot2(bx, by, bz, bx, by, bz);\n"
+						          "\t\t\t// skipped only when neither ray can win; evaluating an object that\n"
+						          "\t\t\t// could have been skipped for one ray does not change its result\n"
+						          "\t\t\tif ((uA <= 0.f || lol_lo(dd) > uA * uA) && (uB <= 0.f || lol_hi(dd) > uB * uB))\n"
+						          "\t\t\t\tcontinue;\n\t\t}\n");
+					else if (k == i)
 						sb_printf(&body,
 						          ") * LOL_F(0x3f808312 /*1.004*/);\n"
 						          "\t\t\tif (u <= 0.f || lol_dot(bx, by, bz, bx, by, bz) > u * u)\n"
 						          "\t\t\t\tcontinue;\n\t\t}\n");
 				}
 				int t = emit_node(&r, s->objects[k]);
-				if (k == i) {
+				if (k == i && two) {
+					char tA[96] = "", tB[96] = "";
+					if (tie_aware) {
+						snprintf(tA, sizeof tA, " || (a_ == bestA && %uu + (lol_u32)i < bidA)", i + 1);
+						snprintf(tB, sizeof tB, " || (b_ == bestB && %uu + (lol_u32)i < bidB)", i + 1);
+					}
+					sb_printf(&body,
+					          "\t\tconst float a_ = lol_lo(t%d), b_ = lol_hi(t%d);\n"
+					          "\t\tif (a_ < bestA%s) {\n\t\t\tbestA = a_;\n\t\t\tbidA = %uu + (lol_u32)i;\n\t\t}\n"
+					          "\t\tif (b_ < bestB%s) {\n\t\t\tbestB = b_;\n\t\t\tbidB = %uu + (lol_u32)i;\n\t\t}\n\t}\n",
+					          t, t, tA, i + 1, tB, i + 1);
+					per_row = r.nrow;
+				} else if (k == i) {
 					if (tie_aware)
 						sb_printf(&body,
 						          "\t\tif (t%d < best || (t%d == best && %uu + (lol_u32)i < bid)) {\n"
@@ -426,14 +482,32 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				sb_printf(&body, "\t{ // object %u: %s\n", k + 1, sigs[k]);
 				g.tmp = 0;
 				int t = emit_node(&g, s->objects[k]);
-				sb_printf(&body,
-				          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu;\n\t\t}\n\t}\n",
-				          t, t, k + 1);
+				if (two)
+					sb_printf(&body,
+					          "\t\tconst float a_ = lol_lo(t%d), b_ = lol_hi(t%d);\n"
+					          "\t\tif (a_ < bestA) {\n\t\t\tbestA = a_;\n\t\t\tbidA = %uu;\n\t\t}\n"
+					          "\t\tif (b_ < bestB) {\n\t\t\tbestB = b_;\n\t\t\tbidB = %uu;\n\t\t}\n\t}\n",
+					          t, t, k + 1, k + 1);
+				else
+					sb_printf(&body,
+					          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu;\n\t\t}\n\t}\n",
+					          t, t, k + 1);
 			}
 		}
 		i = j;
 	}
-	if (fast)
+	if (two)
+		sb_printf(&body,
+		          "\t// Outside the fast forms' ranges (DESIGN.md, guarded fast path) both rays are\n"
+		          "\t// redone the long way, one at a time.\n"
+		          "\tif (!(lo >= LOL_SQRT_FAST_MIN)) {\n"
+		          "\t\tconst lol_u64 rA = %s(lol_lo(x), lol_lo(y), lol_lo(z));\n"
+		          "\t\tconst lol_u64 rB = %s(lol_hi(x), lol_hi(y), lol_hi(z));\n"
+		          "\t\tidA = (lol_u32)(rA >> 32);\n\t\tidB = (lol_u32)(rB >> 32);\n"
+		          "\t\treturn lol_pk(__uint_as_float((lol_u32)rA), __uint_as_float((lol_u32)rB));\n"
+		          "\t}\n\tidA = bidA;\n\tidB = bidB;\n\treturn lol_pk(bestA, bestB);\n}\n",
+		          fallback, fallback);
+	else if (fast)
 		sb_printf(&body,
 		          "\t// The fast forms are bit-identical to IEEE sqrt / division only inside\n"
 		          "\t// these ranges (DESIGN.md, guarded fast path); outside, redo it the long way.\n"
@@ -443,7 +517,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "\t\treturn __uint_as_float((lol_u32)r);\n"
 		          "\t}\n",
 		          fallback);
-	if (packed)
+	if (two)
+		;
+	else if (packed)
 		sb_printf(&body, "\treturn ((lol_u64)bid << 32) | (lol_u64)__float_as_uint(best);\n}\n");
 	else
 		sb_printf(&body, "\tid = bid;\n\treturn best;\n}\n");
@@ -559,24 +635,27 @@ static int guard_pays(const lolb200_scene* s) {
 }
 
 static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
-                     int prune) {
+                     int prune, int two) {
 	struct sb tables = {0};
-	if (guarded == 1 && !guard_pays(s))
+	if (guarded == 1 && !guard_pays(s) && !two)
 		guarded = 0;
 	if (guarded && constants_in_range(s)) {
 		struct sb ref = {0};
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
-		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune);
+		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
 		emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf", "__forceinline__", 1, div_ok,
-		            "lol_sdf_ref", prune);
+		            "lol_sdf_ref", prune, 0);
+		if (two)
+			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf2", "__forceinline__", 1, div_ok,
+			            "lol_sdf_ref", prune, 1);
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
 		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
-		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune);
+		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
@@ -622,6 +701,33 @@ int lolb200_can_cull_backfacing(const lolb200_scene* s) {
 			return 0;
 	}
 	return 1;
+}
+
+/* Does the scene lower to a table loop (a run of >= threshold same-shaped
+ * top-level objects)?  Those are the big scenes, where the two-rays-per-thread
+ * kernel wins (measured on B200: 1024-sphere scene 1.27x; the small example
+ * scenes are 10-20 % slower with it: too few warps to keep the two-wide FMA pipe
+ * busy). */
+static int has_table_loop(const lolb200_scene* s, int threshold) {
+	int found = 0;
+	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
+	for (uint32_t i = 0; i < s->n_objects; i++) {
+		struct sb sig = {0};
+		signature(s, s->objects[i], &sig);
+		sigs[i] = sig.p;
+	}
+	for (uint32_t i = 0; i < s->n_objects && !found;) {
+		uint32_t j = i + 1;
+		while (j < s->n_objects && strcmp(sigs[j], sigs[i]) == 0)
+			j++;
+		if ((int)(j - i) >= threshold)
+			found = 1;
+		i = j;
+	}
+	for (uint32_t i = 0; i < s->n_objects; i++)
+		free(sigs[i]);
+	free(sigs);
+	return found;
 }
 
 /* ------------------------------------------------------------------- driver */
@@ -692,14 +798,21 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		o = *opt;
 	else
 		lolb200_options_default(&o);
-	variant = o.variant ? o.variant : LOLB200_DEFAULT_VARIANT;
-	if (s->n_objects > 65535u)
-		variant = 1; /* variant 2 keeps object ids in 16 bits */
 	threshold = o.loop_threshold > 0 ? o.loop_threshold : 16;
-	if (variant != 1 && variant != 2) {
+	variant = o.variant;
+	if (variant == 0) /* chosen per scene */
+		variant = has_table_loop(s, threshold) ? 3 : LOLB200_DEFAULT_VARIANT;
+	if (variant == 2 && s->n_objects > 65535u)
+		variant = 1; /* variant 2 keeps object ids in 16 bits */
+	if (variant < 1 || variant > 3) {
 		lolb200_set_error("unknown kernel variant %d", variant);
 		return NULL;
 	}
+	/* Variant 3 (two rays per thread, packed FP32) is built from the guarded fast
+	 * forms: it needs exact arithmetic, the guard enabled and every scene constant
+	 * inside the guard's range.  Otherwise variant 1 is what runs. */
+	if (variant == 3 && (o.arith != LOLB200_ARITH_EXACT || !o.guarded_fastpath || !constants_in_range(s)))
+		variant = 1;
 
 	sb_printf(&out, "// Generated by lolb200_lower_cuda (ABI %d) -- do not edit.\n",
 	          LOLB200_ABI_VERSION);
@@ -712,7 +825,24 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_printf(&out, "#define LOL_SHADOW_EARLY %d\n", o.shadow_early_out != 0);
 	sb_printf(&out, "#define LOL_COUNTERS %d\n", o.counters != 0);
 	sb_printf(&out, "#define LOL_VARIANT %d\n", variant);
-	sb_printf(&out, "#define LOL_THREADS %d\n", LOLB200_KERNEL_THREADS);
+	{
+		/* CTA shape.  Variant 3 holds two rays per thread (about twice the
+		 * registers): 128-thread CTAs let the register file be divided more finely. */
+		int threads = o.block_threads > 0 ? o.block_threads : (variant == 3 ? 128 : LOLB200_KERNEL_THREADS);
+		if (threads % 32 || threads > 1024) {
+			lolb200_set_error("block_threads = %d: must be a multiple of 32, at most 1024", threads);
+			free(out.p);
+			return NULL;
+		}
+		/* min_blocks caps the registers; measured best for variant 3: 5 CTAs of 128 */
+		const int min_blocks = o.min_blocks > 0 ? o.min_blocks : (variant == 3 && threads == 128 ? 5 : 0);
+		sb_printf(&out, "#define LOL_THREADS %d\n", threads);
+		if (min_blocks)
+			sb_printf(&out, "#define LOL_LAUNCH_BOUNDS __launch_bounds__(%d, %d)\n", threads, min_blocks);
+		else
+			sb_printf(&out, "#define LOL_LAUNCH_BOUNDS __launch_bounds__(%d)\n", threads);
+		sb_printf(&out, "#define LOL_ROLL_PHASES %d\n", o.roll_phases != 0);
+	}
 	if (variant == 2) {
 		/* struct lol_warp_smem (lol_kernel.cuh): p, n, t|px, dir, sh[lights], id,
 		 * hits, task (+ nsh in instrumented builds), 128 pixels per warp */
@@ -731,7 +861,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
-	         o.prune_bounds != 0);
+	         o.prune_bounds != 0, variant == 3);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

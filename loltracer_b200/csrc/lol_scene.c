@@ -97,6 +97,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->shadow_early_out = 1;
 	o->guarded_fastpath = 1;
 	o->prune_bounds = 1;
+	o->roll_phases = 1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

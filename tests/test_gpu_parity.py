@@ -240,14 +240,16 @@ def test_frames_are_repeatable_and_counter_rearms(scenes_dir):
 
 
 @pytest.mark.parametrize("name", EXAMPLES)
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("guarded", [0, 2])
 def test_kernel_variants_are_bit_identical(name, variant, guarded, scenes_dir):
-    """Phase-sequential vs ray-compaction kernel, IEEE forms vs guarded fast path: the
-    same distance, id and primary step count for every pixel, and the oracle's pixels."""
+    """Phase-sequential vs ray-compaction vs two-rays-per-thread (packed FP32) kernel,
+    IEEE forms vs guarded fast path: the same distance, id and primary step count for
+    every pixel, and the oracle's pixels.  (Variant 3 is built from the guarded forms;
+    with guarded=0 the lowering hands back variant 1.)"""
     import loltracer_b200 as lb
 
-    w, h = 1000, 562  # not a multiple of the 32x4 chunk
+    w, h = 1001, 562  # odd width: a last column without a partner; not a multiple of the chunk
     scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
     want = ol.port_render(scene, w, h, counts=True)
     got = _render(lb, scene, w, h, options=lb.Options.default(variant=variant, guarded_fastpath=guarded))
@@ -255,9 +257,9 @@ def test_kernel_variants_are_bit_identical(name, variant, guarded, scenes_dir):
     assert np.array_equal(got["nprimary"], want["nprimary"])
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_shadow_step_counts_per_variant(variant, scenes_dir):
-    """With the shortcuts off both kernels march exactly the reference's shadow steps."""
+    """With the shortcuts off every kernel marches exactly the reference's shadow steps."""
     import loltracer_b200 as lb
 
     scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
@@ -273,10 +275,10 @@ def test_shadow_step_counts_per_variant(variant, scenes_dir):
     assert (c["primary_evals"], c["normal_evals"], c["shadow_evals"]) == (t["primary"], t["normal"], t["shadow"])
 
 
-@pytest.mark.parametrize("variant", [2])
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("world", [2, 8])
 def test_variant2_shards_and_small_chunks(variant, world, scenes_dir):
-    """Compaction kernel on shards (narrow chunks) and ragged frames."""
+    """Compaction and two-ray kernels on shards (narrow chunks) and ragged frames."""
     import loltracer_b200 as lb
 
     scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
@@ -314,3 +316,23 @@ def test_table_loops_and_pruning_are_exact(name, scenes_dir):
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
     if name != "synthetic":
         _check(a, ol.port_render(scene, w, h))
+
+
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
+def test_two_ray_kernel_4k_bit_identical_to_variant1(name, scenes_dir):
+    """Variant 3 (two pixels per thread in packed FADD2/FMUL2/FFMA2 registers) against
+    variant 1 at 3840x2160: the SAME frame, distances, ids, primary and shadow step
+    counts -- packing changes who issues an instruction, not what it computes."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    w, h = (3840, 2160) if name != "synthetic" else (480, 270)
+    scene = (lb.Scene.from_string(scenegen.synthetic_scene_text()) if name == "synthetic" else
+             lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol")))
+    a = _render(lb, scene, w, h, options=lb.Options.default(variant=1, counters=1))
+    b = _render(lb, scene, w, h, options=lb.Options.default(variant=3, counters=1))
+    assert "#define LOL_VARIANT 3" in lb.lower_cuda(scene, lb.Options.default(variant=3))
+    for key in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+    assert a["renderer"].read_counters() == b["renderer"].read_counters()

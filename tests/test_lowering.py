@@ -36,11 +36,21 @@ def cpu_sdf(tmp_path, src, tag):
     """Compiles everything above the pipeline (helpers + generated lol_sdf) for the host."""
     head = src.split("//@@SCENE@@")[0]
     cu = tmp_path / f"sdf_{tag}.cpp"
+    pair = """
+// the two-rays-per-call form (variant 3): points 2i and 2i+1 share one evaluation
+extern "C" void eval2(const float* p, int n, float* d, unsigned* id) {
+  for (int i = 0; i + 1 < n; i += 2) {
+    const lol_f2 r = lol_sdf2(lol_pk(p[3*i], p[3*i+3]), lol_pk(p[3*i+1], p[3*i+4]),
+                              lol_pk(p[3*i+2], p[3*i+5]), id[i], id[i+1]);
+    d[i] = lol_lo(r); d[i+1] = lol_hi(r);
+  }
+}
+""" if "lol_sdf2(" in head else ""
     cu.write_text(SHIM + head + """
 extern "C" void eval(const float* p, int n, float* d, unsigned* id) {
   for (int i = 0; i < n; ++i) d[i] = lol_sdf(p[3*i], p[3*i+1], p[3*i+2], id[i]);
 }
-""")
+""" + pair)
     so = tmp_path / f"sdf_{tag}.so"
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cu)])
     return C.CDLL(str(so))
@@ -83,6 +93,32 @@ def test_generated_sdf_equals_oracle_on_cpu(name, loops, scenes_dir, tmp_path):
     d = np.zeros(len(pts), np.float32)
     ids = np.zeros(len(pts), np.uint32)
     L.eval(pts.ctypes.data_as(C.c_void_p), len(pts), d.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p))
+    wd, wi = oracle_sdf(scene, pts)
+    assert np.array_equal(d.view(np.uint32), wd.view(np.uint32))
+    assert np.array_equal(ids, wi)
+
+
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
+@pytest.mark.parametrize("loops", [0, 2])
+def test_generated_two_ray_sdf_equals_oracle_on_cpu(name, loops, scenes_dir, tmp_path):
+    """Variant 3's lol_sdf2 evaluates two rays per call (packed FP32 on the GPU; a
+    plain pair under the host shim): each half must equal the oracle's sdf() of its
+    own point, whatever the other half holds -- including far-apart partners, which
+    exercise the pruning test's "skip only if neither ray can win" rule."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, name, scenes_dir)
+    src = lb.lower_cuda(scene, lb.Options.default(variant=3, loop_threshold=loops))
+    assert "#define LOL_VARIANT 3" in src and "lol_sdf2(" in src
+    L = cpu_sdf(tmp_path, src, f"{name}{loops}v3")
+    rng = np.random.default_rng(12)
+    n = 3000 if name != "synthetic" else 300
+    pts = np.concatenate([rng.uniform(-12, 12, (n, 3)), rng.normal(0, 2, (n, 3)) + [0, 1, -6]]).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]  # random partners
+    pts[1] = pts[0]                        # a pair of identical rays
+    d = np.zeros(len(pts), np.float32)
+    ids = np.zeros(len(pts), np.uint32)
+    L.eval2(pts.ctypes.data_as(C.c_void_p), len(pts), d.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p))
     wd, wi = oracle_sdf(scene, pts)
     assert np.array_equal(d.view(np.uint32), wd.view(np.uint32))
     assert np.array_equal(ids, wi)
