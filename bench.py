@@ -152,6 +152,29 @@ def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False, want_tota
     return best, rays, kind, cores, totals
 
 
+def cpu_jit_equivalent(scene_name, w, h, ystride):
+    """JIT-equivalent CPU renderer (stand-in for tracing_jit_renderer.dasc) on the sample."""
+    import tempfile
+
+    import oracle_lib as ol
+    import loltracer_b200 as lb
+
+    scene = load_scene(lb, scene_name)
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        keep = ol.specialised_sdf(scene, tmp)
+        compile_ms = (time.perf_counter() - t0) * 1e3
+        ms = min(ol.port_render(scene, w, h, ystride=ystride, mode=2)["ms"] for _ in range(3))
+        del keep
+    rows = (h + ystride - 1) // ystride
+    rays = rows * w
+    return {"value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": ol.nthreads(), "kind": "port",
+            "what": "oracle pipeline + per-scene straight-line sdf from the lowering, g++ -O2 "
+                    "(stand-in for the DynASM JIT, which needs Lua to build)",
+            "sample": f"every {ystride}th scanline of the same {w}x{h} frame ({rays} rays, {ms:.0f} ms wall)",
+            "ms_per_frame_extrapolated": ms * (w * h / rays), "specialise_and_compile_ms": compile_ms}
+
+
 def run_reference(args, w, h):
     """--impl reference: the reference's CPU implementation of the path, host cores only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -192,6 +215,22 @@ def run_reference(args, w, h):
 
 
 # --------------------------------------------------------------- FLOP model --
+
+
+def ncu_dram_traffic(args, w, h, world):
+    """DRAM bytes of one launch from the committed ncu summary of this very workload, else None."""
+    if world != 1 or args.scene != "scene4" or (w, h) != (3840, 2160) or args.workload != "frame":
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_v1_guarded_scene4_4k.txt")
+    try:
+        total, scale = 0.0, {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(path):
+            if line.strip().startswith("DRAM bytes"):
+                val, unit = line.split("[")[0].split()[-2:]
+                total += float(val) * scale[unit]
+        return total or None
+    except Exception:
+        return None
 
 
 def flops_model(f_sdf, n_lights, pixels, primary, normal, shadow, shaded, rays_marched, rays_culled):
@@ -488,7 +527,11 @@ def main():
                        "MEASURED_PEAKS.json has no FP32 entry; nominal 74.45",
         "frac_of_nominal": achieved_tf / FP32_NOMINAL_TFLOPS,
         "flop_per_launch_executed": exec_flops, "kernel_ms": kernel_ms,
-        "traffic": None,
+        "traffic": ncu_dram_traffic(args, w, h, world),
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one lol_render launch from the committed "
+                        "ncu --set full capture (profiles/); the 33 MB frame stays in the 126 MB L2, so DRAM sees "
+                        "only KBs -- algorithmic HBM bytes are 4 per pixel",
+        "algorithmic_hbm_bytes": w * h * 4,
         "hbm_write_gbs": (w * h * 4 / world) / (kernel_ms * 1e-3) / 1e9,
     }
     try:
@@ -535,6 +578,14 @@ def main():
                                 totals["shadow"] * scale, w * h, w * h * n_lights, 0)
         roofline["achieved_reference_work"] = ref_flops / (kernel_ms * 1e-3) / 1e12
         roofline["flop_per_launch_reference"] = ref_flops
+        # The reference's second CPU renderer, the DynASM tracing JIT, cannot be built in
+        # this image (no Lua for the .dasc preprocessor).  Its stand-in: the same lowering's
+        # straight-line distance code with baked constants, compiled by g++ and driven by the
+        # oracle's pipeline on the same sample (bit-identical frame, tests/test_oracle_pin.py).
+        try:
+            out["cpu_jit_equivalent"] = cpu_jit_equivalent(args.scene, w, h, stride)
+        except Exception as e:  # a missing host compiler must not cost the GPU numbers
+            out["cpu_jit_equivalent"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     if args.all_scenes and world == 1:
         per = {}

@@ -198,7 +198,13 @@ uint64_t lolb200_scene_flops_per_eval(const lolb200_scene* s);
 /* ---------------------------------------------------------- 4. device layer -- */
 
 /* NVRTC for sm_100a; works without a GPU (cross-compile).  Replaces
- * link_and_encode() (tracing_jit_renderer.dasc:60-74).  *image is malloc'ed. */
+ * link_and_encode() (tracing_jit_renderer.dasc:60-74).  *image is malloc'ed.
+ * Environment: LOLB200_CACHE_DIR=<dir> keeps compiled programs as
+ * <dir>/lol-<hash of program text, arithmetic mode, NVRTC version>.cubin and
+ * reuses them (NVRTC costs 0.4-1.1 s per scene); LOLB200_DUMP_DIR=<dir> writes the
+ * program as <dir>/lol-<hash>.cu and compiles it under that name so that
+ * -lineinfo points at a file a profiler can import (the jitdump analogue,
+ * jitdump.c:69-129). */
 int lolb200_compile_cubin(const char* cuda_src, const lolb200_options* o,
                           void** image, size_t* image_size, char** log);
 

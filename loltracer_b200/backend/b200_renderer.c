@@ -88,7 +88,13 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 			 * leave the generated code where a profiler can find it */
 			dump_cuda = "lol-b200-kernel.cu";
 			dump_cubin = "lol-b200-kernel.cubin";
-		} else if (!strcmp(argv[i], "--verbose"))
+		} else if (!strcmp(argv[i], "--cache") && i + 1 < argc)
+			/* compiled kernels are kept here, keyed by a hash of the generated program:
+			 * the next start on the same scene skips NVRTC (lolb200.h, LOLB200_CACHE_DIR) */
+			setenv("LOLB200_CACHE_DIR", argv[++i], 1);
+		else if (!strcmp(argv[i], "--no-cache"))
+			unsetenv("LOLB200_CACHE_DIR");
+		else if (!strcmp(argv[i], "--verbose"))
 			st->verbose = 1;
 		/* anything else belongs to someone else (the JIT backend ignores
 		 * unknown flags too) */

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 #include "lol_internal.h"
@@ -124,6 +125,45 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 			prog_name = path;
 		}
 	}
+	/* LOLB200_CACHE_DIR=<dir>: compiled programs are kept as <dir>/lol-<key>.cubin,
+	 * key = two 64-bit FNV-1a hashes over the program text, the arithmetic mode, the
+	 * NVRTC version and the target.  A hit skips NVRTC (0.4-1.1 s per scene): the
+	 * second start of the viewer on a scene prepares in milliseconds, like the
+	 * CPU JIT does.  (With LOLB200_DUMP_DIR the cache is bypassed: a profiler wants
+	 * the line table to point at the dumped file.) */
+	std::string cache_path;
+	if (const char* dir = getenv("LOLB200_CACHE_DIR")) {
+		if (*dir && !getenv("LOLB200_DUMP_DIR")) {
+			int vmaj = 0, vmin = 0;
+			nvrtcVersion(&vmaj, &vmin);
+			char salt[96];
+			snprintf(salt, sizeof salt, "|sm_100a|nvrtc %d.%d|arith %d|abi %d", vmaj, vmin, opt.arith,
+			         LOLB200_ABI_VERSION);
+			unsigned long long h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;
+			for (const char* part : {src, (const char*)salt})
+				for (const char* c = part; *c; ++c) {
+					h1 = (h1 ^ (unsigned char)*c) * 1099511628211ull;
+					h2 = (h2 ^ ((unsigned char)*c + 0x100)) * 0x100000001b3ull + (h2 >> 29);
+				}
+			char name[64];
+			snprintf(name, sizeof name, "/lol-%016llx%016llx.cubin", h1, h2);
+			cache_path = std::string(dir) + name;
+			if (FILE* f = fopen(cache_path.c_str(), "rb")) {
+				fseek(f, 0, SEEK_END);
+				long n = ftell(f);
+				fseek(f, 0, SEEK_SET);
+				void* buf = n > 4 ? malloc((size_t)n) : nullptr;
+				const bool ok = buf && fread(buf, 1, (size_t)n, f) == (size_t)n && !memcmp(buf, "\177ELF", 4);
+				fclose(f);
+				if (ok) {
+					*image = buf;
+					*image_size = (size_t)n;
+					return LOLB200_OK;
+				}
+				free(buf); /* truncated or foreign file: recompile and replace it */
+			}
+		}
+	}
 	nvrtcProgram prog;
 	nvrtcResult r = nvrtcCreateProgram(&prog, src, prog_name.c_str(), 0, nullptr, nullptr);
 	if (r != NVRTC_SUCCESS) {
@@ -172,6 +212,19 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 	nvrtcGetCUBIN(prog, (char*)*image);
 	*image_size = n;
 	nvrtcDestroyProgram(&prog);
+	if (!cache_path.empty()) {
+		/* written under a private name and renamed, so a concurrent reader (another
+		 * rank preparing the same scene) never sees half a file */
+		char tmp[4200];
+		snprintf(tmp, sizeof tmp, "%s.%ld.tmp", cache_path.c_str(), (long)getpid());
+		if (FILE* f = fopen(tmp, "wb")) {
+			const bool ok = fwrite(*image, 1, n, f) == n;
+			if (fclose(f) == 0 && ok)
+				rename(tmp, cache_path.c_str());
+			else
+				remove(tmp);
+		}
+	}
 	return LOLB200_OK;
 }
 

@@ -13,7 +13,10 @@
  *
  * Plain scalar C, one rounding per operation (-ffp-contract=off, no -mfma), in
  * the operation order of the reference's SSE code.  mode 0 = naive_renderer.c
- * semantics; mode 1 = the deltas of tracing_jit_renderer.dasc (see sdf_jit).
+ * semantics; mode 1 = the deltas of tracing_jit_renderer.dasc (see sdf_jit);
+ * mode 2 = the pipeline of mode 0 around a per-scene SPECIALISED distance
+ * function handed in by the caller (lolo_set_specialised_sdf): the CPU timing
+ * stand-in for the DynASM JIT, which cannot be built here (no Lua).
  */
 #include <math.h>
 #include <pthread.h>
@@ -128,8 +131,20 @@ struct ctx {
 	uint32_t n_primary, n_normal, n_shadow;
 };
 
+/* mode 2: straight-line code with baked constants, generated by the same lowering
+ * that feeds NVRTC and compiled by gcc (tests/oracle_lib.py: specialised_sdf) --
+ * what generate_sdf() (tracing_jit_renderer.dasc:76-216) does with DynASM. */
+typedef float (*lolo_spec_fn)(float x, float y, float z, uint32_t* id);
+static lolo_spec_fn g_spec;
+void lolo_set_specialised_sdf(lolo_spec_fn fn) { g_spec = fn; }
+
 static inline struct world_dist sdf(struct ctx* c, V3 p) {
-	return c->mode ? sdf_jit(c->s, p) : sdf_naive(c->s, p);
+	if (c->mode == 2) {
+		struct world_dist r;
+		r.dist = g_spec(p.x, p.y, p.z, &r.id);
+		return r;
+	}
+	return c->mode == 1 ? sdf_jit(c->s, p) : sdf_naive(c->s, p);
 }
 
 /* get_intersection (naive_renderer.c:47-69) */
@@ -158,12 +173,12 @@ static float softshadow(struct ctx* c, V3 ro, V3 rd, int max_steps, float max_di
 		V3 p = add(ro, scale(rd, dist));
 		float d = sdf(c, p).dist;
 		c->n_shadow++;
-		res = c->mode ? fminf(res, w * d / dist) : minf_(res, w * d / dist);
+		res = c->mode == 1 ? fminf(res, w * d / dist) : minf_(res, w * d / dist);
 		dist += d;
 		if (res < -1 || dist > max_dist)
 			break;
 	}
-	return c->mode ? fmaxf(res, 0.f) : maxf_(res, 0.f);
+	return c->mode == 1 ? fmaxf(res, 0.f) : maxf_(res, 0.f);
 }
 
 /* in_shadow (naive_renderer.c:92-100) */

@@ -28,6 +28,7 @@ def port():
         L.lolo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p] * 6
         L.lolo_sdf.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3),
                                C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+        L.lolo_set_specialised_sdf.argtypes = [C.c_void_p]
         _port = L
     return _port
 
@@ -174,3 +175,67 @@ def compare_frames(got_rgba, got_id, want_rgba, want_id):
     return dict(mask_agree=float(agree.mean()), n_mask_off=int((~agree).sum()),
                 max_rgb_err=max_err, n_rgb_off=int((err[both] > 0).sum()),
                 max_miss_rgb_err=miss_err, id_agree=float((got_id == want_id).mean()))
+
+
+# ---- the generated distance code, compiled for the host -------------------------
+
+HOST_SHIM = r"""
+#define LOL_HOST_SHIM 1
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+typedef unsigned long long lol_u64_shim;
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+#define __constant__ static const
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline float __saturatef(float v) { return (v > 0.f) ? ((v < 1.f) ? v : 1.f) : 0.f; }
+static inline float lol_sqrt_fast(float x) { return std::sqrt(x); }
+static inline float lol_fma(float a, float b, float c) { return std::fma(a, b, c); }
+#define __fmaf_rn lol_fma
+static inline int __float2int_rz(float f) { return (int)f; }
+"""
+
+
+def cpu_sdf(tmp_path, src, tag):
+    """Compiles everything above the pipeline (helpers + generated lol_sdf) for the host:
+    eval/eval2 for tests, lol_spec_sdf for the oracle's mode 2 (the JIT-equivalent CPU baseline)."""
+    import pathlib
+    import subprocess
+    tmp_path = pathlib.Path(tmp_path)
+    head = src.split("//@@SCENE@@")[0]
+    cu = tmp_path / f"sdf_{tag}.cpp"
+    pair = """
+// the two-rays-per-call form (variant 3): points 2i and 2i+1 share one evaluation
+extern "C" void eval2(const float* p, int n, float* d, unsigned* id) {
+  for (int i = 0; i + 1 < n; i += 2) {
+    const lol_f2 r = lol_sdf2(lol_pk(p[3*i], p[3*i+3]), lol_pk(p[3*i+1], p[3*i+4]),
+                              lol_pk(p[3*i+2], p[3*i+5]), id[i], id[i+1]);
+    d[i] = lol_lo(r); d[i+1] = lol_hi(r);
+  }
+}
+""" if "lol_sdf2(" in head else ""
+    cu.write_text(HOST_SHIM + head + """
+extern "C" void eval(const float* p, int n, float* d, unsigned* id) {
+  for (int i = 0; i < n; ++i) d[i] = lol_sdf(p[3*i], p[3*i+1], p[3*i+2], id[i]);
+}
+extern "C" float lol_spec_sdf(float x, float y, float z, unsigned* id) { return lol_sdf(x, y, z, *id); }
+""" + pair)
+    so = tmp_path / f"sdf_{tag}.so"
+    subprocess.check_call(["g++", "-O2", "-msse4.2", "-mavx2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cu)])
+    return C.CDLL(str(so))
+
+
+def specialised_sdf(scene, workdir, tag="spec"):
+    """JIT-equivalent: the lowering's straight-line distance function for `scene`
+    (IEEE forms, constants baked in), compiled by g++ and registered with the oracle
+    as mode 2.  Returns the CDLL (keep it alive while mode 2 is in use)."""
+    import loltracer_b200 as lb
+
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=0, prune_bounds=0))
+    L = cpu_sdf(workdir, src, tag)
+    L.lol_spec_sdf.restype = C.c_float
+    port().lolo_set_specialised_sdf(C.cast(L.lol_spec_sdf, C.c_void_p))
+    return L

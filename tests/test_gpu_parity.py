@@ -336,3 +336,26 @@ def test_two_ray_kernel_4k_bit_identical_to_variant1(name, scenes_dir):
         assert np.array_equal(a[key], b[key]), key
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
     assert a["renderer"].read_counters() == b["renderer"].read_counters()
+
+
+def test_host_surface_follows_a_resizing_window(scenes_dir):
+    """main.c re-fetches the surface every frame and the window is resizable
+    (main.c:182): the host-surface entry point must follow changes of size, pitch and
+    pixel pointer between frames on one renderer (staging frame and pinning are redone)."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    r = lb.Renderer(scene, device=0)
+    keep = []
+    for (w, h, pad) in [(320, 240, 0), (641, 361, 7), (320, 240, 0), (1280, 720, 64), (33, 17, 1)]:
+        host = np.full((h, w + pad), 0xDEADBEEF, np.uint32)
+        keep.append(host)
+        r.render_host(host.ctypes.data, w, h, pitch_bytes=(w + pad) * 4)
+        want = ol.port_render(scene, w, h)
+        got = host[:, :w]
+        err = np.zeros(got.shape, np.int32)
+        for s in (16, 8, 0):
+            err = np.maximum(err, np.abs(((got >> s) & 0xFF).astype(np.int32) - ((want["rgba"] >> s) & 0xFF).astype(np.int32)))
+        assert err.max() <= 1, (w, h)
+        assert (host[:, w:] == 0xDEADBEEF).all(), "padding past the row was written"
+    r.close()

@@ -12,48 +12,7 @@ import pytest
 import oracle_lib as ol
 from conftest import EXAMPLES, ROOT
 
-SHIM = r"""
-#define LOL_HOST_SHIM 1
-#include <cmath>
-#include <cstring>
-#define __device__
-#define __forceinline__ inline
-#define __noinline__
-typedef unsigned long long lol_u64_shim;
-static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
-#define __constant__ static const
-static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
-static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
-static inline float __saturatef(float v) { return (v > 0.f) ? ((v < 1.f) ? v : 1.f) : 0.f; }
-static inline float lol_sqrt_fast(float x) { return std::sqrt(x); }
-static inline float lol_fma(float a, float b, float c) { return std::fma(a, b, c); }
-#define __fmaf_rn lol_fma
-static inline int __float2int_rz(float f) { return (int)f; }
-"""
-
-
-def cpu_sdf(tmp_path, src, tag):
-    """Compiles everything above the pipeline (helpers + generated lol_sdf) for the host."""
-    head = src.split("//@@SCENE@@")[0]
-    cu = tmp_path / f"sdf_{tag}.cpp"
-    pair = """
-// the two-rays-per-call form (variant 3): points 2i and 2i+1 share one evaluation
-extern "C" void eval2(const float* p, int n, float* d, unsigned* id) {
-  for (int i = 0; i + 1 < n; i += 2) {
-    const lol_f2 r = lol_sdf2(lol_pk(p[3*i], p[3*i+3]), lol_pk(p[3*i+1], p[3*i+4]),
-                              lol_pk(p[3*i+2], p[3*i+5]), id[i], id[i+1]);
-    d[i] = lol_lo(r); d[i+1] = lol_hi(r);
-  }
-}
-""" if "lol_sdf2(" in head else ""
-    cu.write_text(SHIM + head + """
-extern "C" void eval(const float* p, int n, float* d, unsigned* id) {
-  for (int i = 0; i < n; ++i) d[i] = lol_sdf(p[3*i], p[3*i+1], p[3*i+2], id[i]);
-}
-""" + pair)
-    so = tmp_path / f"sdf_{tag}.so"
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cu)])
-    return C.CDLL(str(so))
+from oracle_lib import HOST_SHIM as SHIM, cpu_sdf
 
 
 def oracle_sdf(scene, pts):
@@ -203,3 +162,31 @@ def test_compile_error_is_reported():
     with pytest.raises(lb.LolB200Error) as e:
         lb.compile_cubin("this is not CUDA")
     assert e.value.code == -4 and "error" in str(e.value)
+
+
+def test_cubin_cache(scenes_dir, tmp_path, monkeypatch):
+    """LOLB200_CACHE_DIR: the second compilation of the same program is a file read that
+    returns the same image; another program (or arithmetic mode) gets its own entry; a
+    damaged entry is recompiled and replaced."""
+    import time
+
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene2.lol"))
+    src = lb.lower_cuda(scene)
+    monkeypatch.setenv("LOLB200_CACHE_DIR", str(tmp_path))
+    t0 = time.perf_counter()
+    first = lb.compile_cubin(src)
+    t1 = time.perf_counter()
+    again = lb.compile_cubin(src)
+    t2 = time.perf_counter()
+    files = sorted(tmp_path.glob("lol-*.cubin"))
+    assert len(files) == 1 and files[0].read_bytes() == first == again
+    assert (t2 - t1) < (t1 - t0) / 5, "a cache hit must not run NVRTC"
+    fast = lb.Options.default(arith=1)
+    lb.compile_cubin(lb.lower_cuda(scene, fast), fast)
+    lb.compile_cubin(lb.lower_cuda(lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))))
+    assert len(list(tmp_path.glob("lol-*.cubin"))) == 3
+    files[0].write_bytes(b"not a cubin")
+    assert lb.compile_cubin(src) == first and files[0].read_bytes() == first
+    assert not list(tmp_path.glob("*.tmp"))

@@ -150,3 +150,20 @@ def test_jit_semantics_mode(scenes_dir):
     naive, jit = ol.port_render(s4, 160, 90, mode=0), ol.port_render(s4, 160, 90, mode=1)
     cmp = ol.compare_frames(jit["rgba"], jit["id"], naive["rgba"], naive["id"])
     assert cmp["mask_agree"] > 0.999 and cmp["max_rgb_err"] <= 2
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_specialised_sdf_mode_equals_naive(name, scenes_dir, tmp_path):
+    """Mode 2 -- the JIT-equivalent CPU baseline: the oracle's pipeline around the
+    lowering's straight-line distance code compiled by g++ -- renders the naive
+    renderer's frame bit for bit (same semantics, no interpreter dispatch)."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    keep = ol.specialised_sdf(scene, tmp_path, name)
+    naive = ol.port_render(scene, 200, 112, mode=0, counts=True)
+    spec = ol.port_render(scene, 200, 112, mode=2, counts=True)
+    for key in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(naive[key], spec[key]), key
+    assert np.array_equal(naive["dist"].view(np.uint32), spec["dist"].view(np.uint32))
+    assert keep is not None
