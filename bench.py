@@ -54,9 +54,9 @@ def parse_args():
 
 
 def load_scene(lb, name):
-    if name == "synthetic":
+    if name in ("synthetic", "synthetic_csg"):
         from loltracer_b200 import scenegen
-        return lb.Scene.from_string(scenegen.synthetic_scene_text())
+        return lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name == "synthetic_csg"))
     path = name if os.path.exists(name) else os.path.join(ROOT, "tests", "golden", "scenes", name + ".lol")
     return lb.Scene.from_file(path)
 
@@ -132,7 +132,8 @@ def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False, want_tota
     # evaluation counts of the sample (oracle port; also warms the threads up)
     totals = ol.port_render(scene, w, h, ystride=ystride)["totals"] if want_totals else None
     best = None
-    if ol.have_ref() and not force_port and scene_name != "synthetic-port":
+    # the CSG scene uses extension nodes the reference cannot hold: oracle port only
+    if ol.have_ref() and not force_port and scene_name != "synthetic_csg":
         kind = "reference"
         if scene_name == "synthetic":
             from loltracer_b200 import scenegen
@@ -564,7 +565,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         # ~20 core-seconds on scene4: every 4th scanline of the same frame; the
         # 1024-primitive scene costs ~1000x more per ray, so only a few scanlines
-        stride = 4 if args.scene != "synthetic" else max(4, h // 3)
+        stride = 4 if not args.scene.startswith("synthetic") else max(4, h // 3)
         ms, rays, kind, cores, totals = cpu_sample(args.scene, w, h, stride)
         cpu_value = rays / (ms * 1e-3) / 1e6
         out["cpu_baseline"] = {

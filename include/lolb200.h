@@ -54,8 +54,18 @@ enum lolb200_object_type {
 	LOLB200_OBJ_SPHERE = 3,
 	LOLB200_OBJ_BOX = 4,
 	LOLB200_OBJ_PLANE = 5,
-	LOLB200_OBJ_SMOOTH_UNION = 6
+	LOLB200_OBJ_SMOOTH_UNION = 6,
+	/* Extensions beyond the reference grammar (scene.h:27-35 ends at 6; BASELINE
+	 * config C4 asks for "unioned/intersected primitives"): hard CSG nodes with
+	 * children a, b like a smooth union.  union = minf(a, b), intersection =
+	 * maxf(a, b), difference = maxf(a, -b), with float.h's MINSS/MAXSS operand
+	 * rules.  The reference cannot render them, so their oracle is our own
+	 * restatement only (oracle/lol_oracle.c; DESIGN.md "extensions"). */
+	LOLB200_OBJ_UNION = 7,
+	LOLB200_OBJ_INTERSECTION = 8,
+	LOLB200_OBJ_DIFFERENCE = 9
 };
+#define LOLB200_OBJ_HAS_CHILDREN(t) ((t) >= LOLB200_OBJ_SMOOTH_UNION && (t) <= LOLB200_OBJ_DIFFERENCE)
 
 /* scene.h:44-49 */
 typedef struct lolb200_material {

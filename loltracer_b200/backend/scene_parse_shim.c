@@ -60,6 +60,17 @@ static struct vector* shim_defs_from_node(const struct lol_node* n) {
 	return defs;
 }
 
+/* union / intersection / difference are extensions of our front-end; the
+ * reference's struct object (scene.h:58-82) has no place for them. */
+static int shim_has_extension(const struct lol_node* n) {
+	if (n->type == LOL_T_UNION || n->type == LOL_T_INTERSECTION || n->type == LOL_T_DIFFERENCE)
+		return 1;
+	for (size_t i = 0; i < n->ndefs; i++)
+		if (n->defs[i].value.kind == LOL_V_OBJ && shim_has_extension(n->defs[i].value.obj))
+			return 1;
+	return 0;
+}
+
 struct scene* scene_parse_text(const char* text, size_t len) {
 	char err[256];
 	struct lol_doc* doc = lol_parse_text(text, len, err, sizeof err);
@@ -70,6 +81,13 @@ struct scene* scene_parse_text(const char* text, size_t len) {
 		fprintf(stderr, "Error: %s\n", err); /* yyerror, scene-parser.y:193-195 */
 		return NULL;
 	}
+	for (size_t i = 0; i < doc->ncomponents; i++)
+		if (shim_has_extension(&doc->components[i])) {
+			fprintf(stderr, "Error: union/intersection/difference nodes are a lolb200 extension; "
+			                "the reference's scene.c cannot represent them\n");
+			lol_doc_free(doc);
+			return NULL;
+		}
 	materials = vector_new(struct material, 16);
 	for (size_t i = 0; i < doc->nmaterials; i++) { /* scene-parser.y:89-103 */
 		struct vector* defs = shim_defs_from_node(&doc->materials[i]);

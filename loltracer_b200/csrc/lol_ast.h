@@ -25,6 +25,7 @@ enum lol_prop {
 enum lol_type {
 	LOL_T_AMBIENT, LOL_T_CAMERA, LOL_T_POINT_LIGHT, LOL_T_SPHERE, LOL_T_BOX,
 	LOL_T_PLANE, LOL_T_SMOOTH_UNION,
+	LOL_T_UNION, LOL_T_INTERSECTION, LOL_T_DIFFERENCE, /* extensions (lolb200.h) */
 	LOL_T_MATERIAL = 100 /* a `{ ... }` entry of the materials section */
 };
 

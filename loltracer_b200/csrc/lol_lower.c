@@ -217,6 +217,17 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 		coord_minus(g, "y", o->point[1]);
 		sb_printf(g->out, ";\n");
 		return me;
+	case LOLB200_OBJ_UNION:
+	case LOLB200_OBJ_INTERSECTION:
+	case LOLB200_OBJ_DIFFERENCE: { /* extensions: minf(a,b) / maxf(a,b) / maxf(a,-b) */
+		int a = emit_node(g, (uint32_t)o->a);
+		int b = emit_node(g, (uint32_t)o->b);
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst %s t%d = lol_csg_%s(t%d, t%d);\n", g->indent, T, me,
+		          o->type == LOLB200_OBJ_UNION ? "union" :
+		          o->type == LOLB200_OBJ_INTERSECTION ? "inter" : "diff", a, b);
+		return me;
+	}
 	default: { /* sminf(a, b, k), naive_renderer.c:21-24 */
 		int a = emit_node(g, (uint32_t)o->a);
 		int b = emit_node(g, (uint32_t)o->b);
@@ -250,7 +261,8 @@ static void signature(const lolb200_scene* s, uint32_t idx, struct sb* out) {
 	case LOLB200_OBJ_BOX: sb_putn(out, "B", 1); break;
 	case LOLB200_OBJ_PLANE: sb_putn(out, "P", 1); break;
 	default:
-		sb_putn(out, "U(", 2);
+		sb_putn(out, o->type == LOLB200_OBJ_UNION ? "N(" : o->type == LOLB200_OBJ_INTERSECTION ? "I(" :
+		             o->type == LOLB200_OBJ_DIFFERENCE ? "D(" : "U(", 2);
 		signature(s, (uint32_t)o->a, out);
 		sb_putn(out, ",", 1);
 		signature(s, (uint32_t)o->b, out);
@@ -278,9 +290,22 @@ static int bound_node(const lolb200_scene* s, uint32_t idx, double C[3], double*
 		          (double)o->point2[2] * o->point2[2]) + fabs((double)o->radius);
 		return isfinite(*R) && isfinite(C[0]) && isfinite(C[1]) && isfinite(C[2]);
 	case LOLB200_OBJ_PLANE: return 0;
-	default: {
+	case LOLB200_OBJ_DIFFERENCE: /* maxf(a, -b) >= a: a's ball */
+		return bound_node(s, (uint32_t)o->a, C, R);
+	case LOLB200_OBJ_INTERSECTION: { /* maxf(a, b) >= a and >= b: the smaller ball */
+		double Cb[3], Rb;
+		const int ha = bound_node(s, (uint32_t)o->a, C, R);
+		const int hb = bound_node(s, (uint32_t)o->b, Cb, &Rb);
+		if (hb && (!ha || Rb < *R)) {
+			memcpy(C, Cb, sizeof Cb);
+			*R = Rb;
+		}
+		return ha || hb;
+	}
+	default: { /* (smooth) union: the ball around both children's balls (+ k/4) */
 		double Ca[3], Cb[3], Ra, Rb, da = 0, db = 0;
-		if (!(o->smoothness >= 0.f) || !isfinite(o->smoothness))
+		const double k = o->type == LOLB200_OBJ_UNION ? 0.0 : (double)o->smoothness;
+		if (!(k >= 0.0) || !isfinite(k))
 			return 0;
 		if (!bound_node(s, (uint32_t)o->a, Ca, &Ra) || !bound_node(s, (uint32_t)o->b, Cb, &Rb))
 			return 0;
@@ -291,7 +316,7 @@ static int bound_node(const lolb200_scene* s, uint32_t idx, double C[3], double*
 		}
 		da = sqrt(da) + Ra;
 		db = sqrt(db) + Rb;
-		*R = (da > db ? da : db) + 0.25 * (double)o->smoothness;
+		*R = (da > db ? da : db) + 0.25 * k;
 		return 1;
 	}
 	}

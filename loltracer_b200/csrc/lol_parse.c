@@ -40,6 +40,10 @@ static const struct keyword keywords[] = {
 	{"plane", T_TYPE, LOL_T_PLANE},
 	{"smooth_union", T_TYPE, LOL_T_SMOOTH_UNION},
 	{"smooth-union", T_TYPE, LOL_T_SMOOTH_UNION},
+	/* extensions: not in scene-lexer.l */
+	{"union", T_TYPE, LOL_T_UNION},
+	{"intersection", T_TYPE, LOL_T_INTERSECTION},
+	{"difference", T_TYPE, LOL_T_DIFFERENCE},
 	{"shininess", T_PROP, LOL_PROP_SHININESS},
 	{"diffuse", T_PROP, LOL_PROP_DIFFUSE},
 	{"specular", T_PROP, LOL_PROP_SPECULAR},

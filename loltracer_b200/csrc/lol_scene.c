@@ -170,6 +170,9 @@ static int32_t build_object(struct builder* b, const struct lol_node* n) {
 	case LOL_T_BOX: o.type = LOLB200_OBJ_BOX; break;
 	case LOL_T_PLANE: o.type = LOLB200_OBJ_PLANE; break;
 	case LOL_T_SMOOTH_UNION: o.type = LOLB200_OBJ_SMOOTH_UNION; break;
+	case LOL_T_UNION: o.type = LOLB200_OBJ_UNION; break;
+	case LOL_T_INTERSECTION: o.type = LOLB200_OBJ_INTERSECTION; break;
+	case LOL_T_DIFFERENCE: o.type = LOLB200_OBJ_DIFFERENCE; break;
 	default: /* scene.c:277-280 */
 		lolb200_set_error("Unknown scene object (only sphere, box, plane and "
 		                  "smooth_union can be nested)");
@@ -217,7 +220,7 @@ static int32_t build_object(struct builder* b, const struct lol_node* n) {
 			break;
 		case LOL_PROP_A:
 		case LOL_PROP_B:
-			if (o.type == LOLB200_OBJ_SMOOTH_UNION) {
+			if (LOLB200_OBJ_HAS_CHILDREN(o.type)) {
 				ok = 1;
 				if (d->value.kind != LOL_V_OBJ) { /* scene.c:92-97 */
 					lolb200_set_error("property '%s' must be an object",
@@ -244,9 +247,10 @@ static int32_t build_object(struct builder* b, const struct lol_node* n) {
 		o.point[1] = plane_y;
 		o.point[2] = 0.f;
 	}
-	if (o.type == LOLB200_OBJ_SMOOTH_UNION && (o.a < 0 || o.b < 0)) {
+	if (LOLB200_OBJ_HAS_CHILDREN(o.type) && (o.a < 0 || o.b < 0)) {
 		/* the reference would dereference a NULL child at render time */
-		lolb200_set_error("smooth_union needs both 'a' and 'b'");
+		lolb200_set_error("%s needs both 'a' and 'b'",
+		                  o.type == LOLB200_OBJ_SMOOTH_UNION ? "smooth_union" : "a CSG node");
 		b->failed = 1;
 		return -1;
 	}
@@ -454,8 +458,11 @@ int lolb200_scene_check(const lolb200_scene* s) {
 		case LOLB200_OBJ_BOX:
 		case LOLB200_OBJ_PLANE: break;
 		case LOLB200_OBJ_SMOOTH_UNION:
+		case LOLB200_OBJ_UNION:
+		case LOLB200_OBJ_INTERSECTION:
+		case LOLB200_OBJ_DIFFERENCE:
 			if (o->a < 0 || o->b < 0 || (uint32_t)o->a >= i || (uint32_t)o->b >= i) {
-				lolb200_set_error("node %u: smooth union children must precede it", i);
+				lolb200_set_error("node %u: children must precede their parent", i);
 				return LOLB200_EINVAL;
 			}
 			break;
@@ -485,6 +492,10 @@ static uint64_t node_flops(const lolb200_scene* s, uint32_t i) {
 	case LOLB200_OBJ_PLANE: return 1;
 	case LOLB200_OBJ_SMOOTH_UNION:
 		return 13 + node_flops(s, (uint32_t)o->a) + node_flops(s, (uint32_t)o->b);
+	case LOLB200_OBJ_UNION:
+	case LOLB200_OBJ_INTERSECTION:
+	case LOLB200_OBJ_DIFFERENCE: /* one min/max; the negation is free */
+		return 1 + node_flops(s, (uint32_t)o->a) + node_flops(s, (uint32_t)o->b);
 	}
 	return 0;
 }

@@ -37,8 +37,31 @@ def _tree(spheres, k: float, indent: str) -> str:
             f"{indent}\tb = {b}\n{indent}}}")
 
 
+def _csg_tree(cells, rng, k: float, indent: str) -> str:
+    """Balanced smooth_union tree whose leaves are hard CSG pairs (extension nodes): cell
+    2i becomes a lens, intersection { sphere, shifted sphere }, cell 2i+1 a bitten sphere,
+    difference { sphere, shifted sphere } -- two primitives per cell."""
+    if len(cells) == 1:
+        (c, r), kind = cells[0]
+        r = 1.4 * r
+        off = [rng.uniform(-0.6, 0.6) * r for _ in range(3)]
+        c2 = (c[0] + off[0], c[1] + off[1], c[2] + off[2])
+        a = f"sphere {{ point = {_v(c)}, radius = {r:.6f} }}"
+        b = f"sphere {{ point = {_v(c2)}, radius = {0.9 * r:.6f} }}"
+        return f"{kind} {{\n{indent}\ta = {a},\n{indent}\tb = {b}\n{indent}}}"
+    half = len(cells) // 2
+    a = _csg_tree(cells[:half], rng, k, indent + "\t")
+    b = _csg_tree(cells[half:], rng, k, indent + "\t")
+    return (f"smooth_union {{\n{indent}\tsmoothness = {k:.6f},\n{indent}\ta = {a},\n"
+            f"{indent}\tb = {b}\n{indent}}}")
+
+
 def synthetic_scene_text(n_trees: int = 128, leaves: int = 8, seed: int = SYNTHETIC_SEED,
-                         smoothness: float = 0.3) -> str:
+                         smoothness: float = 0.3, csg: bool = False) -> str:
+    """csg=True: BASELINE config C4 as worded ("unioned/intersected primitives"): the same
+    1024 primitives, but every two of them form an intersection or a difference node --
+    extension nodes our front-end adds (include/lolb200.h); the reference's grammar and
+    renderer have none, so only the oracle port can check that scene."""
     rng = random.Random(seed)
     nx, ny, nz = 16, 8, 8
     assert n_trees * leaves <= nx * ny * nz and nx % leaves == 0
@@ -68,7 +91,11 @@ def synthetic_scene_text(n_trees: int = 128, leaves: int = 8, seed: int = SYNTHE
              "specular_intensity = (1, 1.5, 2) }"]
     for t in range(n_trees):
         group = cells[t * leaves:(t + 1) * leaves]
-        tree = _tree(group, smoothness, "\t")
+        if csg:  # two primitives per cell: every other cell of the group
+            kinds = ["intersection", "difference"]
+            tree = _csg_tree([(cell, kinds[i % 2]) for i, cell in enumerate(group[::2])], rng, smoothness, "\t")
+        else:
+            tree = _tree(group, smoothness, "\t")
         # material goes on the top-level node only (naive_renderer.c:102-112)
         head, rest = tree.split("{", 1)
         comps.append(f"\t{head}{{ material = #{1 + t % 4},{rest}")

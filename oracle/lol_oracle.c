@@ -62,6 +62,20 @@ static inline float sminf_(float a, float b, float k) {
 	return l - k * h * (1.f - h);
 }
 
+/* Extension nodes (lolb200.h: union / intersection / difference).  The reference
+ * has no such nodes: this is OUR definition, restated once here and once in the
+ * lowering -- parity for them is against this file only ("unpinned"). */
+static float csg_dist(const lolb200_scene* s, const lolb200_object* o, V3 p,
+                      float (*rec)(const lolb200_scene*, const lolb200_object*, V3)) {
+	float a = rec(s, &s->nodes[o->a], p);
+	float b = rec(s, &s->nodes[o->b], p);
+	switch (o->type) {
+	case LOLB200_OBJ_UNION: return minf_(a, b);
+	case LOLB200_OBJ_INTERSECTION: return maxf_(a, b);
+	default: return maxf_(a, -b); /* difference */
+	}
+}
+
 /* get_obj_dist (naive_renderer.c:10-28) with sdSphere / sdRoundBox (sdf.h:8-22).
  * Children of a smooth union see p, not p - point. */
 static float obj_dist(const lolb200_scene* s, const lolb200_object* o, V3 p) {
@@ -74,6 +88,9 @@ static float obj_dist(const lolb200_scene* s, const lolb200_object* o, V3 p) {
 		return len(c) + minf_(maxf_(d.x, maxf_(d.y, d.z)), 0.f) - o->radius;
 	}
 	case LOLB200_OBJ_PLANE: return q.y;
+	case LOLB200_OBJ_UNION:
+	case LOLB200_OBJ_INTERSECTION:
+	case LOLB200_OBJ_DIFFERENCE: return csg_dist(s, o, p, obj_dist);
 	default: {
 		float a = obj_dist(s, &s->nodes[o->a], p);
 		float b = obj_dist(s, &s->nodes[o->b], p);
@@ -102,6 +119,9 @@ static float obj_dist_jit(const lolb200_scene* s, const lolb200_object* o, V3 p)
 	case LOLB200_OBJ_SPHERE: return len(q) - o->radius;
 	case LOLB200_OBJ_BOX: return INFINITY;
 	case LOLB200_OBJ_PLANE: return q.y;
+	case LOLB200_OBJ_UNION:
+	case LOLB200_OBJ_INTERSECTION:
+	case LOLB200_OBJ_DIFFERENCE: return csg_dist(s, o, p, obj_dist_jit);
 	default: {
 		float a = obj_dist_jit(s, &s->nodes[o->a], p);
 		float b = obj_dist_jit(s, &s->nodes[o->b], p);

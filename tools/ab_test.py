@@ -16,12 +16,12 @@ configs = sys.argv[3:] or [""]
 frame = torch.zeros((h, w), dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 for name in names:
-    scene = (lb.Scene.from_string(scenegen.synthetic_scene_text()) if name == "synthetic" else
+    scene = (lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name.endswith("csg"))) if name.startswith("synthetic") else
              lb.Scene.from_file(os.path.join(ROOT, "tests", "golden", "scenes", name + ".lol")))
     for cfg in configs:
         kw = dict(kv.split("=") for kv in cfg.split(",") if kv)
         r = lb.Renderer(scene, lb.Options.default(**{k: int(v) for k, v in kw.items()}))
-        n = 3 if name == "synthetic" else 20
+        n = 3 if name.startswith("synthetic") else 20
         for _ in range(2):
             r.render_device(frame.data_ptr(), w, h, stream=st)
         torch.cuda.synchronize()

@@ -10,9 +10,9 @@ import loltracer_b200 as lb
 
 name, w, h, variant, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
 arith = int(sys.argv[6]) if len(sys.argv) > 6 else 0
-if name == "synthetic":
+if name.startswith("synthetic"):
     from loltracer_b200 import scenegen
-    scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
+    scene = lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name.endswith("csg")))
 else:
     scene = lb.Scene.from_file(os.path.join(ROOT, "tests", "golden", "scenes", name + ".lol"))
 extra = dict(kv.split("=") for kv in os.environ.get("LOL_OPTS", "").split(",") if kv)
