@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--scene", default="scene4")
     ap.add_argument("--size", default=None, help="default 3840x2160 (frame) / 7680x4320 (orbit)")
     ap.add_argument("--gather", default="peer", choices=["nccl", "peer"])
+    ap.add_argument("--e2e-path", default="host-shards", choices=["host-shards", "gather-then-copy"],
+                    help="N > 1, e2e leg: every rank copies its own bands into one shared-memory host frame over "
+                         "its own PCIe link (default), or the frame is gathered on rank 0 and copied from there")
     ap.add_argument("--workload", default="frame", choices=["frame", "orbit"],
                     help="frame: one frame per step, sharded by bands over the GPUs (configs C1-C4); "
                          "orbit: one step = 64 camera-orbit frames, whole frames dealt to the GPUs (C5)")
@@ -471,11 +474,27 @@ def main():
         del check
 
     # ---- e2e: host buffers, D2H inside the timed region ----
+    # N = 1: lolb200_render_host, the call b200_renderer.c makes.  N > 1: the frame has to end
+    # up in HOST memory, so by default no GPU gathers anything: every rank renders its bands and
+    # its own copy engine writes them into one POSIX shared-memory frame (rank 0 created it, all
+    # ranks map and pin it): 1/N of the bytes per PCIe link instead of all of them through rank
+    # 0's (lolb200_render_host_shard; the in-process twin is `--gather host` of the C backend).
     host = torch.empty((h, w), dtype=torch.int32).pin_memory() if rank == 0 else None
+    shared, shared_path, e2e_verified = None, None, None
+    if world > 1 and args.e2e_path == "host-shards":
+        import numpy as np
+        shared_path = f"/dev/shm/lolb200_bench_{os.environ.get('MASTER_PORT', '0')}_{w}x{h}"
+        if rank == 0:
+            np.memmap(shared_path, dtype=np.uint32, mode="w+", shape=(h, w)).flush()
+        dist.barrier()
+        shared = np.memmap(shared_path, dtype=np.uint32, mode="r+", shape=(h, w))
 
     def e2e_step():
         if world == 1:
             renderer.render_host(host.data_ptr(), w, h)
+        elif shared is not None:
+            renderer.render_host_shard(shared.ctypes.data, w, h, shard)  # returns when this rank's rows are in
+            dist.barrier()                                               # the frame is complete for everyone
         else:
             step()
             if rank == 0:
@@ -495,6 +514,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
     e2e_value = w * h / (e2e_ms * 1e-3) / 1e6
+    if shared is not None:
+        if rank == 0:
+            import numpy as np
+            e2e_verified = bool(np.array_equal(np.asarray(shared), frame.cpu().numpy().view(np.uint32)))
+        dist.barrier()
+        del shared
+        if rank == 0:
+            os.unlink(shared_path)
 
     # ---- executed work (instrumented twin of the kernel, untimed) ----
     copt = lb.Options.default(variant=args.variant, arith=1 if args.arith == "fast" else 0, counters=1)
@@ -552,7 +579,13 @@ def main():
                    "l2": "256 MB write between timed steps (untimed); the kernel reads no global inputs",
                    "kernel": renderer.kernel_info()},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
-                "h2d_bytes_per_step": 192, "d2h_bytes_per_step": w * h * 4},
+                "h2d_bytes_per_step": 192 * world, "d2h_bytes_per_step": w * h * 4,
+                "path": ("lolb200_render_host: slab launches overlapped with the read-back into a pinned host frame"
+                         if world == 1 else
+                         "lolb200_render_host_shard on every rank: own bands over own PCIe link into one "
+                         "shared-memory host frame, then a barrier" if args.e2e_path == "host-shards" else
+                         "frame gathered on rank 0 over NVLink, then one D2H copy from rank 0"),
+                "host_frame_equals_single_gpu": e2e_verified},
         "gpu_launches": n_launches,
         "sharded_frame_equals_single_gpu": verified,
         "roofline": roofline,

@@ -291,6 +291,14 @@ int lolb200_read_counters(lolb200_renderer* r, uint64_t out[8]);
 int lolb200_deinterleave_device(const void* gathered_dev, void* frame_dev, int w, int h,
                                 int world, int band_rows, size_t shard_pixels,
                                 size_t pitch_px, void* stream);
+/* One rank's bands of the frame, end to end into the FULL-FRAME host surface
+ * `pixels` (row y of the frame at pixels + y * pitch_bytes): render, then the
+ * rank's own copy engine writes each 4-row band to its final rows.  Ranks of a
+ * multi-process job hand in the same shared-memory surface; nothing crosses
+ * NVLink.  Synchronous for this rank. */
+int lolb200_render_host_shard(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                              const lolb200_pixfmt* fmt, const lolb200_shard* shard, void* pixels,
+                              size_t pitch_bytes);
 /* Pixels a rank's compact buffer needs (bands padded so every rank is equal). */
 size_t lolb200_shard_pixels(int w, int h, int world, int band_rows);
 
@@ -302,9 +310,14 @@ size_t lolb200_shard_pixels(int w, int h, int world, int band_rows);
  *   LOLB200_GATHER_PEER: every device's kernel stores its bands straight into
  *                        devices[0]'s frame through peer access.
  * render_host then copies the frame into the caller's surface like
- * lolb200_render_host does.  Calls of one group must come from one thread at a
- * time (the frame leader of b200_renderer.c). */
-enum { LOLB200_GATHER_NCCL = 0, LOLB200_GATHER_PEER = 1 };
+ * lolb200_render_host does.
+ *   LOLB200_GATHER_HOST: no device-side gather at all: every device copies its
+ *                        own bands into the caller's (pinned, portable) surface
+ *                        over its own PCIe link -- the fastest way to a frame
+ *                        in HOST memory, which is what renderer.h asks for.
+ * Calls of one group must come from one thread at a time (the frame leader of
+ * b200_renderer.c). */
+enum { LOLB200_GATHER_NCCL = 0, LOLB200_GATHER_PEER = 1, LOLB200_GATHER_HOST = 2 };
 typedef struct lolb200_group lolb200_group; /* opaque */
 int lolb200_group_create(const lolb200_scene* s, const lolb200_options* o, const int* devices,
                          int n_devices, int gather, lolb200_group** out);

@@ -129,6 +129,8 @@ def lib() -> C.CDLL:
         "lolb200_scene_parse_string": (i32, [C.c_char_p, sz, C.POINTER(C.POINTER(SceneStruct))]),
         "lolb200_scene_clone": (C.POINTER(SceneStruct), [C.POINTER(SceneStruct)]),
         "lolb200_scene_free": (None, [C.POINTER(SceneStruct)]),
+        "lolb200_render_host_shard": (i32, [vp, C.POINTER(Camera), i32, i32, C.POINTER(PixFmt), C.POINTER(Shard),
+                                            vp, sz]),
         "lolb200_camera_basis_compute": (None, [C.POINTER(Camera), i32, i32, C.POINTER(CameraBasis)]),
         "lolb200_options_default": (None, [C.POINTER(Options)]),
         "lolb200_lower_cuda": (vp, [C.POINTER(SceneStruct), C.POINTER(Options), C.POINTER(sz)]),
@@ -327,6 +329,14 @@ class Renderer:
                                          C.byref(fmt) if fmt else None, pixels_ptr,
                                          pitch_bytes or w * 4))
 
+    def render_host_shard(self, pixels_ptr: int, w: int, h: int, shard: Shard,
+                          camera: Optional[Camera] = None, pitch_bytes: Optional[int] = None,
+                          fmt: Optional[PixFmt] = None) -> None:
+        """This rank's bands, end to end into the full-frame host surface (own PCIe link)."""
+        _check(lib().lolb200_render_host_shard(self._h, C.byref(camera) if camera else None, w, h,
+                                               C.byref(fmt) if fmt else None, C.byref(shard), pixels_ptr,
+                                               pitch_bytes or w * 4))
+
     def read_counters(self) -> dict:
         out = (C.c_uint64 * 8)()
         _check(lib().lolb200_read_counters(self._h, C.byref(out)))
@@ -338,7 +348,7 @@ class Renderer:
 class Group:
     """Several GPUs driven by one process (what b200_renderer.c --gpus N uses)."""
 
-    GATHER = {"nccl": 0, "peer": 1}
+    GATHER = {"nccl": 0, "peer": 1, "host": 2}
 
     def __init__(self, scene: Scene, n_devices: int, gather: str = "nccl",
                  options: Optional[Options] = None, devices: Optional[Sequence[int]] = None):

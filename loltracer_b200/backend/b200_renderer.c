@@ -63,6 +63,7 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 	lolb200_scene* flat;
 
 	lolb200_options_default(&st->options);
+	st->gather = LOLB200_GATHER_HOST;
 	for (int i = 3; i < argc; i++) {
 		if (!strcmp(argv[i], "--exact"))
 			st->options.arith = LOLB200_ARITH_EXACT;
@@ -77,8 +78,13 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 			st->device = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--gpus") && i + 1 < argc)
 			st->gpus = atoi(argv[++i]);
-		else if (!strcmp(argv[i], "--gather") && i + 1 < argc)
-			st->gather = !strcmp(argv[++i], "peer") ? LOLB200_GATHER_PEER : LOLB200_GATHER_NCCL;
+		else if (!strcmp(argv[i], "--gather") && i + 1 < argc) {
+			/* host (default): every GPU copies its own bands into surf->pixels over its own
+			 * PCIe link; nccl / peer: the frame is first completed on the first GPU over NVLink */
+			const char* m = argv[++i];
+			st->gather = !strcmp(m, "peer") ? LOLB200_GATHER_PEER :
+			             !strcmp(m, "nccl") ? LOLB200_GATHER_NCCL : LOLB200_GATHER_HOST;
+		}
 		else if (!strcmp(argv[i], "--dump-cuda") && i + 1 < argc)
 			dump_cuda = argv[++i];
 		else if (!strcmp(argv[i], "--dump-cubin") && i + 1 < argc)
@@ -104,8 +110,8 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 	 * are baked into the kernel here; the camera is re-read every frame. */
 	flat = lolb200_scene_from_reference(data->scene);
 	if (st->gpus > 1) {
-		/* the image is sharded in cyclic 4-row bands over GPUs device..device+N-1
-		 * and gathered on the first one over NVLink */
+		/* the image is sharded in cyclic 4-row bands over GPUs device..device+N-1;
+		 * st->gather says how the bands reach surf->pixels */
 		int devices[64];
 		if (st->gpus > 64)
 			st->gpus = 64;

@@ -530,6 +530,41 @@ extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* 
 	return launch_bands(r, cam, w, h, fmt, shard, dst_dev, pitch_px, aux, stream, 0, 0, 0);
 }
 
+/* Pin the caller's surface once (SDL hands back the same pixels until the
+ * window is resized) so the read-back is DMA at PCIe speed.  Portable: every
+ * device of an in-process group copies into the same surface.  A surface that
+ * somebody else already pinned (the group, or another renderer of this process)
+ * is used as it is. */
+static void pin_surface(lolb200_renderer* r, void* pixels, size_t bytes) {
+	if (r->registered == pixels && r->registered_bytes == bytes)
+		return;
+	if (r->registered) {
+		cudaHostUnregister(r->registered);
+		r->registered = nullptr;
+	}
+	r->registered_dev = nullptr;
+	r->registered_bytes = 0;
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+		if (cudaHostGetDevicePointer(&r->registered_dev, pixels, 0) != cudaSuccess) {
+			cudaGetLastError();
+			r->registered_dev = nullptr;
+		}
+		return; /* pinned by someone else: not ours to unregister */
+	}
+	cudaGetLastError();
+	if (cudaHostRegister(pixels, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess) {
+		r->registered = pixels;
+		r->registered_bytes = bytes;
+		if (cudaHostGetDevicePointer(&r->registered_dev, pixels, 0) != cudaSuccess) {
+			cudaGetLastError();
+			r->registered_dev = nullptr;
+		}
+	} else {
+		cudaGetLastError(); /* pageable copy still works, only slower */
+	}
+}
+
 extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
                                    const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes) {
 	if (!r || !pixels || w <= 0 || h <= 0 || pitch_bytes < (size_t)w * 4) {
@@ -545,26 +580,7 @@ extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* ca
 		CUDA_TRY(cudaMalloc(&r->frame, need * sizeof(lol_u32)));
 		r->frame_pixels = need;
 	}
-	/* Pin the caller's surface once (SDL hands back the same pixels until the
-	 * window is resized) so the read-back is one DMA at PCIe speed. */
-	const size_t bytes = pitch_bytes * (size_t)h;
-	if (r->registered != pixels || r->registered_bytes != bytes) {
-		if (r->registered) {
-			cudaHostUnregister(r->registered);
-			r->registered = nullptr;
-		}
-		r->registered_dev = nullptr;
-		if (cudaHostRegister(pixels, bytes, cudaHostRegisterMapped) == cudaSuccess) {
-			r->registered = pixels;
-			r->registered_bytes = bytes;
-			if (cudaHostGetDevicePointer(&r->registered_dev, pixels, 0) != cudaSuccess) {
-				cudaGetLastError();
-				r->registered_dev = nullptr;
-			}
-		} else {
-			cudaGetLastError(); /* pageable copy still works, only slower */
-		}
-	}
+	pin_surface(r, pixels, pitch_bytes * (size_t)h);
 	const char* mode = getenv("LOLB200_HOST_MODE");
 	if (mode && !strcmp(mode, "mapped") && r->registered_dev && pitch_bytes % 4 == 0) {
 		/* zero-copy: the kernel stores pixels straight into the pinned surface */
@@ -605,6 +621,87 @@ extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* ca
 	}
 	CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
 	return LOLB200_OK;
+}
+
+/* One rank's share of a frame, straight into the (full-frame) host surface: the
+ * rank renders its cyclic 4-row bands into a compact staging buffer and its own
+ * copy engine writes each band to its final rows of `pixels`.  With one GPU per
+ * rank every GPU uses its own PCIe link and NVLink is not involved at all -- for
+ * a frame that has to end up in HOST memory (what renderer.h asks for) this
+ * beats gathering on GPU 0 first and pushing 33 MB through one link.
+ * enqueue: no synchronisation; wait: the rank's pixels are in host memory. */
+static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                              const lolb200_pixfmt* fmt, const lolb200_shard* shard, void* pixels,
+                              size_t pitch_bytes, cudaEvent_t start_after) {
+	if (!r || !pixels || !shard || w <= 0 || h <= 0 || pitch_bytes < (size_t)w * 4 || shard->world < 1 ||
+	    shard->rank < 0 || shard->rank >= shard->world) {
+		lolb200_set_error("lolb200_render_host_shard: bad argument");
+		return LOLB200_EINVAL;
+	}
+	DeviceGuard g(r->device);
+	const size_t world = (size_t)shard->world, rank = (size_t)shard->rank;
+	const size_t need = lolb200_shard_pixels(w, h, shard->world, 0);
+	if (r->frame_pixels < need) {
+		cudaFree(r->frame);
+		r->frame = nullptr;
+		r->frame_pixels = 0;
+		CUDA_TRY(cudaMalloc(&r->frame, need * sizeof(lol_u32)));
+		r->frame_pixels = need;
+	}
+	pin_surface(r, pixels, pitch_bytes * (size_t)h);
+	const size_t bands = ((size_t)h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
+	const size_t local_bands = bands > rank ? (bands - rank + world - 1) / world : 0;
+	if (local_bands == 0)
+		return LOLB200_OK;
+	lolb200_shard sh = *shard;
+	sh.band_rows = LOL_BAND_ROWS;
+	sh.dst_full_frame = 0;
+	size_t slabs = LOL_MAX_SLABS;
+	if (local_bands < slabs * 16)
+		slabs = local_bands / 16 ? local_bands / 16 : 1;
+	const size_t per = (local_bands + slabs - 1) / slabs;
+	for (size_t k = 0, b0 = 0; b0 < local_bands; ++k, b0 += per) {
+		const size_t nb = b0 + per <= local_bands ? per : local_bands - b0;
+		if (start_after)
+			CUDA_TRY(cudaStreamWaitEvent(r->slab_stream[k], start_after, 0));
+		int rc = launch_bands(r, cam, w, h, fmt, &sh, r->frame, (size_t)w, nullptr, r->slab_stream[k],
+		                      b0, nb, (int)k);
+		if (rc != LOLB200_OK)
+			return rc;
+		CUDA_TRY(cudaEventRecord(r->slab_done[k], r->slab_stream[k]));
+		CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->slab_done[k], 0));
+		/* row j of every band of the slab: one strided 2-D copy (source rows are
+		 * 4*w apart in the compact buffer, destination rows world*4 surface rows) */
+		for (size_t j = 0; j < LOL_BAND_ROWS; ++j) {
+			size_t rows = 0; /* local bands of the slab whose row j is inside the frame */
+			for (size_t lb = b0 + nb; lb > b0; --lb)
+				if ((((lb - 1) * world + rank) * LOL_BAND_ROWS + j) < (size_t)h) {
+					rows = lb - b0;
+					break;
+				}
+			if (!rows)
+				continue;
+			const size_t y0 = (b0 * world + rank) * LOL_BAND_ROWS + j;
+			CUDA_TRY(cudaMemcpy2DAsync((char*)pixels + y0 * pitch_bytes, world * LOL_BAND_ROWS * pitch_bytes,
+			                           r->frame + (b0 * LOL_BAND_ROWS + j) * (size_t)w,
+			                           (size_t)LOL_BAND_ROWS * w * 4, (size_t)w * 4, rows,
+			                           cudaMemcpyDeviceToHost, r->copy_stream));
+		}
+	}
+	return LOLB200_OK;
+}
+
+static int host_shard_wait(lolb200_renderer* r) {
+	DeviceGuard g(r->device);
+	CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_render_host_shard(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
+                                         const lolb200_pixfmt* fmt, const lolb200_shard* shard,
+                                         void* pixels, size_t pitch_bytes) {
+	int rc = host_shard_enqueue(r, cam, w, h, fmt, shard, pixels, pitch_bytes, nullptr);
+	return rc != LOLB200_OK ? rc : host_shard_wait(r);
 }
 
 extern "C" int lolb200_read_counters(lolb200_renderer* r, uint64_t out[8]) {
@@ -859,7 +956,7 @@ extern "C" void lolb200_group_destroy(lolb200_group* g) {
 
 extern "C" int lolb200_group_create(const lolb200_scene* s, const lolb200_options* o,
                                     const int* devices, int n, int gather, lolb200_group** out) {
-	if (!s || !out || n < 1 || n > 64 || (gather != LOLB200_GATHER_NCCL && gather != LOLB200_GATHER_PEER)) {
+	if (!s || !out || n < 1 || n > 64 || (gather != LOLB200_GATHER_NCCL && gather != LOLB200_GATHER_PEER && gather != LOLB200_GATHER_HOST)) {
 		lolb200_set_error("lolb200_group_create: bad argument");
 		return LOLB200_EINVAL;
 	}
@@ -961,22 +1058,47 @@ extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera*
 	}
 	if (g->n == 1)
 		return lolb200_render_host(g->renderers[0], cam, w, h, fmt, pixels, pitch_bytes);
-	int rc = group_resize(g, w, h);
-	if (rc != LOLB200_OK)
-		return rc;
 	cudaSetDevice(g->devices[0]);
 	const size_t bytes = pitch_bytes * (size_t)h;
 	if (g->registered != pixels || g->registered_bytes != bytes) {
 		if (g->registered)
 			cudaHostUnregister(g->registered);
 		g->registered = nullptr;
-		if (cudaHostRegister(pixels, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+		if (cudaHostRegister(pixels, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
 			g->registered = pixels;
 			g->registered_bytes = bytes;
 		} else {
 			cudaGetLastError();
 		}
 	}
+	if (g->gather == LOLB200_GATHER_HOST) {
+		/* every GPU renders its bands and copies them into the surface over its own
+		 * PCIe link; nothing crosses NVLink */
+		CUDA_TRY(cudaEventRecord(g->t0, g->streams[0]));
+		for (int i = 0; i < g->n; ++i) {
+			lolb200_shard sh = {i, g->n, 0, 0};
+			int rc = host_shard_enqueue(g->renderers[i], cam, w, h, fmt, &sh, pixels, pitch_bytes,
+			                            i ? g->t0 : nullptr);
+			if (rc != LOLB200_OK)
+				return rc;
+		}
+		for (int i = 0; i < g->n; ++i) {
+			int rc = host_shard_wait(g->renderers[i]);
+			if (rc != LOLB200_OK)
+				return rc;
+		}
+		cudaSetDevice(g->devices[0]);
+		CUDA_TRY(cudaEventRecord(g->t1, g->streams[0]));
+		CUDA_TRY(cudaStreamSynchronize(g->streams[0]));
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, g->t0, g->t1) == cudaSuccess)
+			g->last_ms = ms;
+		return LOLB200_OK;
+	}
+	int rc = group_resize(g, w, h);
+	if (rc != LOLB200_OK)
+		return rc;
+	cudaSetDevice(g->devices[0]);
 	CUDA_TRY(cudaEventRecord(g->t0, g->streams[0]));
 	for (int i = 0; i < g->n; ++i) {
 		lolb200_shard sh = {i, g->n, 0, g->gather == LOLB200_GATHER_PEER ? 1 : 0};

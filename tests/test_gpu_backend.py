@@ -48,7 +48,7 @@ def test_backend_dumps_generated_code(scenes_dir, tmp_path):
     assert (tmp_path / "lol-b200-kernel.cubin").read_bytes()[:4] == b"\x7fELF"
 
 
-@pytest.mark.parametrize("gather", ["nccl", "peer"])
+@pytest.mark.parametrize("gather", ["nccl", "peer", "host"])
 def test_backend_on_all_gpus_of_the_box(gather, scenes_dir, tmp_path):
     """--gpus N: one host process drives every GPU; same frame as one GPU.  Needs >= 2 GPUs
     (gpurun --gpus 2); on a single-GPU box it is skipped."""
@@ -82,7 +82,7 @@ def test_group_api_matches_single_gpu(scenes_dir):
     one = np.zeros((h, w), np.uint32)
     r = lb.Renderer(scene)
     r.render_host(one.ctypes.data, w, h)
-    for gather in ("nccl", "peer"):
+    for gather in ("nccl", "peer", "host"):
         g = lb.Group(scene, n, gather)
         got = np.zeros((h, w), np.uint32)
         for _ in range(2):

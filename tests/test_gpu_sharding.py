@@ -61,3 +61,26 @@ def test_full_frame_destination(world, scenes_dir):
     torch.cuda.synchronize()
     assert torch.equal(frame, full)
     r.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("size,pad", [((640, 360), 0), ((333, 129), 5), ((64, 7), 0), ((1920, 1080), 0)])
+def test_ranks_copy_their_own_bands_into_one_host_surface(world, size, pad, scenes_dir):
+    """lolb200_render_host_shard: each rank renders its cyclic bands and ITS copy engine
+    writes them to their final rows of the full-frame host surface (strided 2-D copies,
+    ragged last band, foreign pitch).  All ranks run on this one GPU here; on an 8-GPU box
+    the same calls come from eight processes with a shared-memory surface (bench.py)."""
+    import loltracer_b200 as lb
+
+    w, h = size
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    r = lb.Renderer(scene, device=0)
+    want = np.zeros((h, w), np.uint32)
+    r.render_host(want.ctypes.data, w, h)
+    host = np.full((h, w + pad), 0xDEADBEEF, np.uint32)
+    for rank in range(world):
+        r.render_host_shard(host.ctypes.data, w, h, lb.Shard(rank=rank, world=world),
+                            pitch_bytes=(w + pad) * 4)
+    assert np.array_equal(host[:, :w], want)
+    assert (host[:, w:] == 0xDEADBEEF).all()
+    r.close()
