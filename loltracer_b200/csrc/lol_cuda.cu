@@ -656,10 +656,14 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 	lolb200_shard sh = *shard;
 	sh.band_rows = LOL_BAND_ROWS;
 	sh.dst_full_frame = 0;
-	size_t slabs = LOL_MAX_SLABS;
+	/* fewer slabs as the shard shrinks: with eight ranks the copy is a quarter of
+	 * the kernel and every slab costs the (single) leader thread API calls */
+	size_t slabs = LOL_MAX_SLABS / world >= 2 ? LOL_MAX_SLABS / world : 2;
 	if (local_bands < slabs * 16)
 		slabs = local_bands / 16 ? local_bands / 16 : 1;
 	const size_t per = (local_bands + slabs - 1) / slabs;
+	/* whole bands with rows back to back in the surface: one copy per slab */
+	const bool one_copy = pitch_bytes == (size_t)w * 4 && h % LOL_BAND_ROWS == 0;
 	for (size_t k = 0, b0 = 0; b0 < local_bands; ++k, b0 += per) {
 		const size_t nb = b0 + per <= local_bands ? per : local_bands - b0;
 		if (start_after)
@@ -670,6 +674,14 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 			return rc;
 		CUDA_TRY(cudaEventRecord(r->slab_done[k], r->slab_stream[k]));
 		CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->slab_done[k], 0));
+		if (one_copy) {
+			const size_t y0 = (b0 * world + rank) * LOL_BAND_ROWS;
+			CUDA_TRY(cudaMemcpy2DAsync((char*)pixels + y0 * pitch_bytes, world * LOL_BAND_ROWS * pitch_bytes,
+			                           r->frame + b0 * LOL_BAND_ROWS * (size_t)w,
+			                           (size_t)LOL_BAND_ROWS * w * 4, (size_t)LOL_BAND_ROWS * w * 4, nb,
+			                           cudaMemcpyDeviceToHost, r->copy_stream));
+			continue;
+		}
 		/* row j of every band of the slab: one strided 2-D copy (source rows are
 		 * 4*w apart in the compact buffer, destination rows world*4 surface rows) */
 		for (size_t j = 0; j < LOL_BAND_ROWS; ++j) {
