@@ -191,7 +191,9 @@ typedef struct lolb200_options {
 	                            lights are loops around ONE copy of the distance
 	                            code each (instruction-cache footprint), 0 =
 	                            unrolled; -1... not used; default 1             */
-	int32_t reserved[4];
+	int32_t prune_group;     /* tuning: objects per group of the two-level box
+	                            pruning in table loops; 0 = default (8)         */
+	int32_t reserved[3];
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

@@ -209,19 +209,24 @@ def cpu_sdf(tmp_path, src, tag):
     cu = tmp_path / f"sdf_{tag}.cpp"
     pair = """
 // the two-rays-per-call form (variant 3): points 2i and 2i+1 share one evaluation
+// hints: whatever won at the previous pair -- arbitrary for random points, and the result
+// must not depend on them
 extern "C" void eval2(const float* p, int n, float* d, unsigned* id) {
+  unsigned ha = 0, hb = 0;
   for (int i = 0; i + 1 < n; i += 2) {
     const lol_f2 r = lol_sdf2(lol_pk(p[3*i], p[3*i+3]), lol_pk(p[3*i+1], p[3*i+4]),
-                              lol_pk(p[3*i+2], p[3*i+5]), id[i], id[i+1]);
+                              lol_pk(p[3*i+2], p[3*i+5]), ha, hb, id[i], id[i+1]);
     d[i] = lol_lo(r); d[i+1] = lol_hi(r);
+    ha = id[i + 1]; hb = (i % 6 == 0) ? id[i] : 0u;   // crossed over, sometimes none
   }
 }
 """ if "lol_sdf2(" in head else ""
     cu.write_text(HOST_SHIM + head + """
 extern "C" void eval(const float* p, int n, float* d, unsigned* id) {
-  for (int i = 0; i < n; ++i) d[i] = lol_sdf(p[3*i], p[3*i+1], p[3*i+2], id[i]);
+  unsigned hint = 0;  // the previous point's winner: arbitrary here, must not matter
+  for (int i = 0; i < n; ++i) { d[i] = lol_sdf(p[3*i], p[3*i+1], p[3*i+2], hint, id[i]); hint = (i % 5) ? id[i] : 0u; }
 }
-extern "C" float lol_spec_sdf(float x, float y, float z, unsigned* id) { return lol_sdf(x, y, z, *id); }
+extern "C" float lol_spec_sdf(float x, float y, float z, unsigned* id) { return lol_sdf(x, y, z, 0u, *id); }
 """ + pair)
     so = tmp_path / f"sdf_{tag}.so"
     subprocess.check_call(["g++", "-O2", "-msse4.2", "-mavx2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cu)])

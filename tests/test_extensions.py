@@ -86,7 +86,7 @@ def test_csg_synthetic_scene_lowers_to_one_table_loop(tmp_path):
     scene = lb.Scene.from_string(scenegen.synthetic_scene_text(csg=True))
     assert scene.struct.n_objects == 129 and scene.flops_per_eval() == 128 * (8 * 10 + 4 + 3 * 13 + 1) + 2
     src = lb.lower_cuda(scene)
-    assert "128 x U(U(I(S,S),D(S,S)),U(I(S,S),D(S,S)))" in src and "cannot win" in src
+    assert "128 x U(U(I(S,S),D(S,S)),U(I(S,S),D(S,S)))" in src and "none can win" in src
     for variant in (1, 3):
         L = ol.cpu_sdf(tmp_path, lb.lower_cuda(scene, lb.Options.default(variant=variant)), f"csg{variant}")
         rng = np.random.default_rng(7)

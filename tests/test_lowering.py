@@ -44,7 +44,7 @@ def test_generated_sdf_equals_oracle_on_cpu(name, loops, scenes_dir, tmp_path):
     scene = _scene(lb, name, scenes_dir)
     src = lb.lower_cuda(scene, lb.Options.default(guarded_fastpath=2, loop_threshold=loops))
     if loops == 2 and name in ("scene", "scene2"):
-        assert "cannot win" in src  # scene: 2 spheres, scene2: 3 spheres in a row
+        assert "none can win" in src and "lol_box_skips(" in src  # scene: 2 spheres, scene2: 3 spheres in a row
     L = cpu_sdf(tmp_path, src, f"{name}{loops}")
     rng = np.random.default_rng(11)
     n = 3000 if name != "synthetic" else 300
