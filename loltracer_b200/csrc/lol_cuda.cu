@@ -350,6 +350,14 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 		if (th)
 			r->threads = atoi(th + strlen("#define LOL_THREADS "));
 		const char* sm = strstr(r->source.c_str(), "#define LOL_SMEM_PER_WARP ");
+		const char* tw = strstr(r->source.c_str(), "#define LOL_TAB_WORDS ");
+		if (r->variant != 2 && tw && strstr(r->source.c_str(), "#define LOL_TAB_IN_SMEM 1")) {
+			/* the kernel copies its loop tables into shared memory (lol_lower.c: struct tabs) */
+			r->dyn_smem = (size_t)atol(tw + strlen("#define LOL_TAB_WORDS ")) * sizeof(lol_u32);
+			CREATE_TRY(cudaFuncSetAttribute((const void*)r->kernel,
+			                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                (int)r->dyn_smem));
+		}
 		if (r->variant == 2 && sm) {
 			r->dyn_smem = (size_t)atol(sm + strlen("#define LOL_SMEM_PER_WARP ")) *
 			              (r->threads / 32);

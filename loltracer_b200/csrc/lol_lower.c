@@ -449,17 +449,52 @@ static void group_box(float (*boxes)[LOL_BOUND_SLOTS], const uint32_t* members, 
 	out[6] = (float)m;
 }
 
+/* ---- the constant tables of table loops: ONE array of words ---------------------
+ * Every table (rows, group boxes, id -> row) is a range of lol_tables[]; its name
+ * is a macro `(LOL_TAB + offset)`.  LOL_TAB is the array itself (__constant__, or
+ * global memory above 56 KB), or -- on the GPU, when it fits -- a copy in SHARED
+ * memory that every CTA makes once (lol_kernel.cuh): the loops read their rows with
+ * register-indexed loads, which cost a constant-cache lookup each (ncu: short-
+ * scoreboard stalls 4.3 per issue, 20 % lookup misses on the 31 KB table of the
+ * 1024-sphere scene) and a plain LDS from shared memory. */
+struct tabs {
+	struct sb words, defs;
+	size_t n;
+};
+
+static void tab_start(struct tabs* T, const char* fmt, int run_no) {
+	char name[64];
+	while (T->n % 4) { /* 16-byte aligned: vector loads */
+		sb_printf(&T->words, "0u, ");
+		T->n++;
+	}
+	snprintf(name, sizeof name, fmt, run_no);
+	sb_printf(&T->defs, "#define %s (LOL_TAB + %zu)\n", name, T->n);
+	sb_printf(&T->words, "\n\t/* %s */\n", name);
+}
+
+static void tab_float(struct tabs* T, float f) {
+	sb_bits(&T->words, f);
+	sb_printf(&T->words, ", ");
+	T->n++;
+}
+
+static void tab_u32(struct tabs* T, uint32_t v) {
+	sb_printf(&T->words, "%uu, ", v);
+	T->n++;
+}
+
 /* One distance function.  fast = 0: the reference form (IEEE sqrt and division as
  * the compiler emits them), named `name`.  fast = 1: the guarded form, which
  * runs the same arithmetic without the per-operation special-case branches and
  * hands the whole evaluation to `fallback` when its one range check fails. */
 static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_scene* s,
                         int loop_threshold, const char* name, const char* attrs, int fast,
-                        int div_ok, const char* fallback, int prune, int two) {
-	struct sb body = {0}, tables = {0};
+                        int div_ok, const char* fallback, int prune, int two, int smem_ok) {
+	struct sb body = {0};
+	struct tabs tables = {{0}, {0}, 0};
 	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok, .two = two};
 	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
-	size_t table_bytes = 0;
 	int run_no = 0;
 
 	for (uint32_t i = 0; i < s->n_objects; i++) {
@@ -529,7 +564,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			sb_printf(&body, "\t// objects %u..%u: %u x %s\n", i + 1, j, n, sigs[i]);
 			if (!prune) {
 				/* plain loop in file order; row r belongs to object id i + 1 + r */
-				sb_printf(&tables, "LOL_TABLE_SPACE lol_u32 lol_run%d[] = {\n", run_no);
+				tab_start(&tables, "lol_run%d", run_no);
 				for (uint32_t k = i; k < j; k++) {
 					struct sb scratch = {0};
 					struct cgen r = {.s = s, .out = (k == i) ? &body : &scratch, .in_loop = 1,
@@ -553,17 +588,13 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          t, t, i + 1);
 					if (k == i)
 						per_row = r.nrow;
-					sb_printf(&tables, "\t");
-					for (size_t q = 0; q < r.nrow; q++) {
-						sb_bits(&tables, r.row[q]);
-						sb_printf(&tables, ", ");
-					}
-					sb_printf(&tables, "\n");
+					sb_printf(&tables.words, "\n\t");
+					for (size_t q = 0; q < r.nrow; q++)
+						tab_float(&tables, r.row[q]);
 					free(r.row);
 					free(scratch.p);
 				}
-				sb_printf(&tables, "};\n#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
-				table_bytes += per_row * n * sizeof(float);
+				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
 				run_no++;
 			} else {
 				/* Pruned loop.  The rows are sorted along a Morton curve through their box
@@ -584,22 +615,21 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				for (uint32_t q = 0; q < n; q++)
 					rowof[order[q]] = q;
 				/* tables: groups, id -> row, rows */
-				sb_printf(&tables, "LOL_TABLE_SPACE lol_u32 lol_run%d_groups[] = {\n", run_no);
+				tab_start(&tables, "lol_run%d_groups", run_no);
 				for (uint32_t g0 = 0; g0 < n; g0 += LOL_GROUP) {
 					float gb[LOL_BOUND_SLOTS];
 					group_box(boxes, order + g0, g0 + LOL_GROUP <= n ? LOL_GROUP : n - g0, gb);
-					sb_printf(&tables, "\t");
-					for (int q = 0; q < LOL_BOUND_SLOTS; q++) {
-						sb_bits(&tables, gb[q]);
-						sb_printf(&tables, ", ");
-					}
-					sb_printf(&tables, "\n");
+					sb_printf(&tables.words, "\n\t");
+					for (int q = 0; q < LOL_BOUND_SLOTS; q++)
+						tab_float(&tables, gb[q]);
 				}
-				sb_printf(&tables, "};\nLOL_TABLE_SPACE lol_u32 lol_run%d_rowof[] = {", run_no);
-				for (uint32_t k = 0; k < n; k++)
-					sb_printf(&tables, "%s%u,", k % 16 ? " " : "\n\t", rowof[k]);
-				sb_printf(&tables, "\n};\nLOL_TABLE_SPACE lol_u32 lol_run%d[] = {\n", run_no);
-				table_bytes += (size_t)ngroups * LOL_BOUND_SLOTS * 4 + (size_t)n * 4;
+				tab_start(&tables, "lol_run%d_rowof", run_no);
+				for (uint32_t k = 0; k < n; k++) {
+					if (k % 16 == 0)
+						sb_printf(&tables.words, "\n\t");
+					tab_u32(&tables, rowof[k]);
+				}
+				tab_start(&tables, "lol_run%d", run_no);
 
 				for (uint32_t q = 0; q < n; q++) {
 					const uint32_t k = i + order[q];
@@ -681,17 +711,13 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          t, t, t);
 					if (q == 0)
 						per_row = r.nrow;
-					sb_printf(&tables, "\t");
-					for (size_t w = 0; w < r.nrow; w++) {
-						sb_bits(&tables, r.row[w]);
-						sb_printf(&tables, ", ");
-					}
-					sb_printf(&tables, "\n");
+					sb_printf(&tables.words, "\n\t");
+					for (size_t w = 0; w < r.nrow; w++)
+						tab_float(&tables, r.row[w]);
 					free(r.row);
 					free(scratch.p);
 				}
-				sb_printf(&tables, "};\n#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
-				table_bytes += per_row * n * sizeof(float);
+				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
 				run_no++;
 				free(boxes);
 				free(order);
@@ -746,11 +772,25 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		sb_printf(&body, "\tid = bid;\n\treturn best;\n}\n");
 
 	if (tables_out) {
+		const size_t table_bytes = tables.n * 4;
 		/* 64 KB of __constant__ space; keep a margin for the kernel parameters. */
-		sb_printf(tables_out, "#define LOL_TABLE_SPACE %s\n",
-		          table_bytes <= 56 * 1024 ? "__constant__" : "__device__ const");
-		if (tables.p)
-			sb_putn(tables_out, tables.p, tables.len);
+		sb_printf(tables_out, "#define LOL_TABLE_SPACE %s\n#define LOL_TAB_WORDS %zu\n",
+		          table_bytes <= 56 * 1024 ? "__constant__" : "__device__ const", tables.n);
+		if (tables.n) {
+			sb_printf(tables_out, "LOL_TABLE_SPACE __align__(16) lol_u32 lol_tables[] = {");
+			sb_putn(tables_out, tables.words.p, tables.words.len);
+			sb_printf(tables_out, "\n};\n");
+			/* up to 96 KB of shared memory per CTA for the copy (two CTAs per SM still fit) */
+			if (smem_ok && table_bytes <= 96 * 1024)
+				sb_printf(tables_out,
+				          "#ifdef LOL_HOST_SHIM\n#define LOL_TAB lol_tables\n#else\n"
+				          "// every CTA copies the tables into shared memory once (lol_render's prologue)\n"
+				          "extern __shared__ __align__(16) lol_u32 lol_tab_smem[];\n"
+				          "#define LOL_TAB lol_tab_smem\n#define LOL_TAB_IN_SMEM 1\n#endif\n");
+			else
+				sb_printf(tables_out, "#define LOL_TAB lol_tables\n");
+			sb_putn(tables_out, tables.defs.p, tables.defs.len);
+		}
 	}
 	sb_putn(out, body.p, body.len);
 
@@ -758,7 +798,8 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		free(sigs[i]);
 	free(sigs);
 	free(body.p);
-	free(tables.p);
+	free(tables.words.p);
+	free(tables.defs.p);
 }
 
 /* ------------------------------------------------- guarded fast path proofs */
@@ -856,7 +897,7 @@ static int guard_pays(const lolb200_scene* s) {
 }
 
 static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
-                     int prune, int two) {
+                     int prune, int two, int smem_ok) {
 	struct sb tables = {0};
 	if (guarded == 1 && !guard_pays(s) && !two)
 		guarded = 0;
@@ -864,19 +905,19 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		struct sb ref = {0};
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
-		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0);
+		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
 		emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf", "__forceinline__", 1, div_ok,
-		            "lol_sdf_ref", prune, 0);
+		            "lol_sdf_ref", prune, 0, smem_ok);
 		if (two)
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf2", "__forceinline__", 1, div_ok,
-			            "lol_sdf_ref", prune, 1);
+			            "lol_sdf_ref", prune, 1, smem_ok);
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
 		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
-		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0);
+		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
@@ -925,10 +966,13 @@ int lolb200_can_cull_backfacing(const lolb200_scene* s) {
 }
 
 /* Does the scene lower to a table loop (a run of >= threshold same-shaped
- * top-level objects)?  Those are the big scenes, where the two-rays-per-thread
- * kernel wins (measured on B200: 1024-sphere scene 1.27x; the small example
- * scenes are 10-20 % slower with it: too few warps to keep the two-wide FMA pipe
- * busy). */
+ * top-level objects)?  A BRUTE-FORCE loop over a big scene is where the two-rays-
+ * per-thread kernel wins (measured on B200, 1024 spheres, pruning off: 1.38x).
+ * With the pruned loops (boxes, groups, hints) a ray computes only a handful of
+ * objects and the pair loses again: both rays of a thread must agree to skip, and
+ * there are half as many warps to hide the table loads (4K: 50.6 vs 47.8 ms,
+ * 1080p: 25.4 vs 13.8 ms).  The small example scenes are 10-20 % slower with it
+ * (DESIGN.md).  So: variant 3 only for unpruned table loops. */
 static int has_table_loop(const lolb200_scene* s, int threshold) {
 	int found = 0;
 	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
@@ -1023,7 +1067,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	lol_group = o.prune_group > 0 ? (uint32_t)o.prune_group : 8u;
 	variant = o.variant;
 	if (variant == 0) /* chosen per scene */
-		variant = has_table_loop(s, threshold) ? 3 : LOLB200_DEFAULT_VARIANT;
+		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;
 	if (variant == 2 && s->n_objects > 65535u)
 		variant = 1; /* variant 2 keeps object ids in 16 bits */
 	if (variant < 1 || variant > 3) {
@@ -1083,7 +1127,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
-	         o.prune_bounds != 0, variant == 3);
+	         o.prune_bounds != 0, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

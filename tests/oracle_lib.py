@@ -189,6 +189,7 @@ HOST_SHIM = r"""
 typedef unsigned long long lol_u64_shim;
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 #define __constant__ static const
+#define __align__(n) __attribute__((aligned(n)))
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __saturatef(float v) { return (v > 0.f) ? ((v < 1.f) ? v : 1.f) : 0.f; }

@@ -126,7 +126,11 @@ def test_synthetic_scene_becomes_a_table_loop():
 
     scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
     src = lb.lower_cuda(scene)
-    assert "lol_run0[]" in src and "128 x U(U(U(S,S),U(S,S)),U(U(S,S),U(S,S)))" in src
+    assert "#define lol_run0 (LOL_TAB + " in src and "128 x U(U(U(S,S),U(S,S)),U(U(S,S),U(S,S)))" in src
+    # rows, group boxes and the id -> row map live in ONE array that the kernel copies to shared memory
+    assert "lol_run0_groups" in src and "lol_run0_rowof" in src and "#define LOL_TAB_IN_SMEM 1" in src
+    words = int(re.search(r"#define LOL_TAB_WORDS (\d+)", src).group(1))
+    assert 128 * 50 < words < 128 * 70
     assert src.count("lol_len(") + src.count("lol_sqrt_fast(") < 40  # one unrolled tree, not 1024 spheres
     unrolled = lb.lower_cuda(scene, lb.Options.default(loop_threshold=100000))
     assert unrolled.count("lol_len(") > 1024
