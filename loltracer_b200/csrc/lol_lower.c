@@ -449,6 +449,198 @@ static void group_box(float (*boxes)[LOL_BOUND_SLOTS], const uint32_t* members, 
 	out[6] = (float)m;
 }
 
+/* Cost of one object in the FLOP convention of DESIGN.md (sphere 10, round box 20,
+ * plane 1, smooth node 13, CSG node 1): what a skipped evaluation saves. */
+static unsigned node_cost(const lolb200_scene* s, uint32_t idx) {
+	const lolb200_object* o = &s->nodes[idx];
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: return 10;
+	case LOLB200_OBJ_BOX: return 20;
+	case LOLB200_OBJ_PLANE: return 1;
+	case LOLB200_OBJ_SMOOTH_UNION:
+		return 13 + node_cost(s, (uint32_t)o->a) + node_cost(s, (uint32_t)o->b);
+	default: return 1 + node_cost(s, (uint32_t)o->a) + node_cost(s, (uint32_t)o->b);
+	}
+}
+/* a box test is about 20 instructions: worth it from two spheres' worth of work on */
+#define LOL_TEST_PAYS 20u
+
+/* ---- does a box test pay?  a sampled estimate ----------------------------------
+ * A test costs about 20 instructions on every evaluation and saves the object only
+ * where it fires; whether that is often depends on where rays actually go (scene4:
+ * 42 % of all evaluations skip the blob; scene3, whose blob fills the view: almost
+ * none, and the tests cost 21 %).  So the lowering marches a coarse frame of the
+ * scene's own camera on the CPU -- primary rays and the shadow rays of every hit,
+ * the steps render_thread would take -- and counts how often each test would fire.
+ * Plain float arithmetic: this steers an optimisation that is exact either way, it
+ * need not round like the reference. */
+static float est_node(const lolb200_scene* s, uint32_t idx, const float p[3]) {
+	const lolb200_object* o = &s->nodes[idx];
+	const float q[3] = {p[0] - o->point[0], p[1] - o->point[1], p[2] - o->point[2]};
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: return sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) - o->radius;
+	case LOLB200_OBJ_BOX: {
+		const float d[3] = {fabsf(q[0]) - o->point2[0], fabsf(q[1]) - o->point2[1], fabsf(q[2]) - o->point2[2]};
+		const float c[3] = {fmaxf(d[0], 0.f), fmaxf(d[1], 0.f), fmaxf(d[2], 0.f)};
+		return sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) + fminf(fmaxf(d[0], fmaxf(d[1], d[2])), 0.f) -
+		       o->radius;
+	}
+	case LOLB200_OBJ_PLANE: return q[1];
+	default: {
+		const float a = est_node(s, (uint32_t)o->a, p), b = est_node(s, (uint32_t)o->b, p);
+		if (o->type == LOLB200_OBJ_UNION)
+			return fminf(a, b);
+		if (o->type == LOLB200_OBJ_INTERSECTION)
+			return fmaxf(a, b);
+		if (o->type == LOLB200_OBJ_DIFFERENCE)
+			return fmaxf(a, -b);
+		const float h = fminf(fmaxf(.5f + .5f * (b - a) / o->smoothness, 0.f), 1.f);
+		return (b + (a - b) * h) - o->smoothness * h * (1.f - h);
+	}
+	}
+}
+
+static int est_box_skips(const float p[3], const float b[7], float best) {
+	const float q[3] = {fmaxf(fabsf(p[0] - b[0]) - b[3], 0.f), fmaxf(fabsf(p[1] - b[1]) - b[4], 0.f),
+	                    fmaxf(fabsf(p[2] - b[2]) - b[5], 0.f)};
+	const float u = (best + b[6]) * 1.004f;
+	return u > 0.f && q[0] * q[0] + q[1] * q[1] + q[2] * q[2] > u * u;
+}
+
+struct est {
+	const lolb200_scene* s;
+	const unsigned char* straight; /* per object: evaluated in straight-line code */
+	float (*boxes)[LOL_BOUND_SLOTS];
+	const uint32_t* bounded;       /* the bounded straight-line objects */
+	uint32_t nb;
+	const float* all;              /* the box around them */
+	unsigned long points, all_fires, *reached, *fires; /* per bounded object */
+};
+
+/* sdf() at p as the generated code would run it with every test on, counting. */
+static float est_sdf(struct est* e, const float p[3]) {
+	const lolb200_scene* s = e->s;
+	float best = INFINITY;
+	for (uint32_t k = 0; k < s->n_objects; k++) { /* the objects without a box come first */
+		int is_bounded = 0;
+		for (uint32_t q = 0; q < e->nb; q++)
+			is_bounded |= e->bounded[q] == k;
+		if (e->straight[k] && !is_bounded)
+			best = fminf(best, est_node(s, s->objects[k], p));
+	}
+	e->points++;
+	if (est_box_skips(p, e->all, best))
+		e->all_fires++;
+	for (uint32_t q = 0; q < e->nb; q++) { /* own tests see the running minimum */
+		const uint32_t k = e->bounded[q];
+		e->reached[q]++;
+		if (est_box_skips(p, e->boxes[k], best))
+			e->fires[q]++;
+		best = fminf(best, est_node(s, s->objects[k], p));
+	}
+	for (uint32_t k = 0; k < s->n_objects; k++) /* table loops */
+		if (!e->straight[k])
+			best = fminf(best, est_node(s, s->objects[k], p));
+	return best;
+}
+
+static void est_march(struct est* e) {
+	const lolb200_scene* s = e->s;
+	const int w = s->n_nodes > 256 ? 24 : 64, h = s->n_nodes > 256 ? 14 : 36;
+	lolb200_camera_basis cb;
+	lolb200_camera_basis_compute(&s->camera, w, h, &cb);
+	for (int y = 0; y < h; y++)
+		for (int x = 0; x < w; x++) {
+			const float vx = ((float)x + .5f) / (float)w * 2.f - 1.f, vy = 1.f - ((float)y + .5f) / (float)h * 2.f;
+			float rd[3], t = 0.f;
+			for (int c = 0; c < 3; c++)
+				rd[c] = cb.right[c] * (vx * cb.width) + cb.up[c] * (vy * cb.height) + cb.dir[c];
+			const float inv = 1.f / sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+			for (int c = 0; c < 3; c++)
+				rd[c] *= inv;
+			for (int i = 0; i < 256; i++) { /* get_intersection, naive_renderer.c:47-69 */
+				const float p[3] = {cb.origin[0] + rd[0] * t, cb.origin[1] + rd[1] * t, cb.origin[2] + rd[2] * t};
+				const float d = est_sdf(e, p);
+				t += d;
+				if (!(d >= 0.001f) || !(t <= 100.f))
+					break;
+			}
+			if (!(t < 100.f))
+				continue;
+			const float hit[3] = {cb.origin[0] + rd[0] * t, cb.origin[1] + rd[1] * t, cb.origin[2] + rd[2] * t};
+			for (uint32_t l = 0; l < s->n_lights; l++) { /* softshadow, naive_renderer.c:72-100 */
+				float dir[3] = {s->lights[l].point[0] - hit[0], s->lights[l].point[1] - hit[1],
+				                s->lights[l].point[2] - hit[2]};
+				const float dist = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+				float st = 0.f, res = 1.f;
+				if (!(dist > 0.f))
+					continue;
+				for (int c = 0; c < 3; c++)
+					dir[c] /= dist;
+				for (int i = 0; i < 128; i++) {
+					const float p[3] = {hit[0] + dir[0] * (1.f + st), hit[1] + dir[1] * (1.f + st),
+					                    hit[2] + dir[2] * (1.f + st)};
+					const float d = est_sdf(e, p);
+					if (st > 0.f)
+						res = fminf(res, 50.f * d / st);
+					st += d;
+					if (!(res > 0.f) || !(st <= dist) || !(d == d))
+						break;
+				}
+			}
+		}
+}
+
+/* `lol_box_skips(x, y, z, <box as immediates>, best...)` */
+static void emit_box_test(struct cgen* g, const float box[7], int two) {
+	sb_printf(g->out, "lol_box_skips%s(x, y, z", two ? "2" : "");
+	for (int q = 0; q < 7; q++) {
+		sb_printf(g->out, ", ");
+		cst(g, box[q]);
+	}
+	sb_printf(g->out, two ? ", bestA, bestB)" : ", best)");
+}
+
+/* One straight-line top-level object: `{ evaluate; update the running minimum }`.
+ * tie_aware: the update also takes an equal distance from a smaller id (needed when
+ * something with a larger id may have been evaluated before).  own_box: the object
+ * is skipped when its bounding box proves it cannot win. */
+static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, const char* sig,
+                                 int two, int tie_aware, const float* own_box, const char* tabs) {
+	char ind[16];
+	snprintf(ind, sizeof ind, "%s\t", tabs);
+	g->indent = ind;
+	g->tmp = 0;
+	sb_printf(body, "%s{ // object %u: %s\n", tabs, k + 1, sig);
+	if (own_box) {
+		sb_printf(body, "%s\t// dist(object, p) >= dbox(p) - M >= best: cannot win\n%s\tif (!", tabs, tabs);
+		emit_box_test(g, own_box, two);
+		sb_printf(body, ") {\n");
+		snprintf(ind, sizeof ind, "%s\t\t", tabs);
+	}
+	int t = emit_node(g, g->s->objects[k]);
+	if (two) {
+		char tA[64] = "", tB[64] = "";
+		if (tie_aware) {
+			snprintf(tA, sizeof tA, " || (a_ == bestA && %uu < bidA)", k + 1);
+			snprintf(tB, sizeof tB, " || (b_ == bestB && %uu < bidB)", k + 1);
+		}
+		sb_printf(body,
+		          "%sconst float a_ = lol_lo(t%d), b_ = lol_hi(t%d);\n"
+		          "%sif (a_ < bestA%s) {\n%s\tbestA = a_;\n%s\tbidA = %uu;\n%s}\n"
+		          "%sif (b_ < bestB%s) {\n%s\tbestB = b_;\n%s\tbidB = %uu;\n%s}\n",
+		          ind, t, t, ind, tA, ind, ind, k + 1, ind, ind, tB, ind, ind, k + 1, ind);
+	} else if (tie_aware)
+		sb_printf(body, "%sif (t%d < best || (t%d == best && %uu < bid)) {\n%s\tbest = t%d;\n%s\tbid = %uu;\n%s}\n",
+		          ind, t, t, k + 1, ind, t, ind, k + 1, ind);
+	else
+		sb_printf(body, "%sif (t%d < best) {\n%s\tbest = t%d;\n%s\tbid = %uu;\n%s}\n", ind, t, ind, t, ind,
+		          k + 1, ind);
+	if (own_box)
+		sb_printf(body, "%s\t}\n", tabs);
+	sb_printf(body, "%s}\n", tabs);
+}
+
 /* ---- the constant tables of table loops: ONE array of words ---------------------
  * Every table (rows, group boxes, id -> row) is a range of lol_tables[]; its name
  * is a macro `(LOL_TAB + offset)`.  LOL_TAB is the array itself (__constant__, or
@@ -545,14 +737,90 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 	 * and tighten `best`, which is what the loops' bounding-ball test compares
 	 * against); the update rule of a loop then breaks ties by object id, so the
 	 * result is the reference's "first of equal distances" whatever the order. */
+	if (prune) {
+		/* Straight-line objects, reordered: first the ones without a box (planes: one
+		 * subtraction, and they give `best` a finite value), then the bounded ones --
+		 * all of them behind ONE test of the box around them when that pays, and each
+		 * expensive one behind its own.  On scene4 the five-sphere blob (105 FLOP) is
+		 * skipped in 42 % of all evaluations: wherever a ray is nearer to the floor
+		 * than to the blob's box (simulated on the march points of a 192x108 frame). */
+		const uint32_t no = s->n_objects;
+		unsigned char* straight = calloc(no ? no : 1, 1);
+		float(*boxes)[LOL_BOUND_SLOTS] = malloc(sizeof *boxes * (no ? no : 1));
+		uint32_t* bounded = malloc(sizeof *bounded * (no ? no : 1));
+		uint32_t nb = 0;
+		unsigned total = 0;
+		for (uint32_t i = 0; i < no;) {
+			uint32_t j = i + 1;
+			while (j < no && strcmp(sigs[j], sigs[i]) == 0)
+				j++;
+			if ((int)(j - i) < loop_threshold)
+				memset(straight + i, 1, j - i);
+			i = j;
+		}
+		for (uint32_t k = 0; k < no; k++) {
+			if (!straight[k])
+				continue;
+			bound_row(s, s->objects[k], boxes[k]);
+			if (isfinite(boxes[k][3]) && isfinite(boxes[k][4]) && isfinite(boxes[k][5])) {
+				bounded[nb++] = k;
+				total += node_cost(s, s->objects[k]);
+			} else
+				emit_straight_object(&body, &g, k, sigs[k], two, 0, NULL, "\t");
+		}
+		if (nb) {
+			float all[LOL_BOUND_SLOTS];
+			unsigned char* own = calloc(nb, 1);
+			int wrap = 0;
+			group_box(boxes, bounded, nb, all);
+			if (total >= LOL_TEST_PAYS) {
+				/* instructions saved where a test fires (about 1.5 per FLOP of the convention),
+				 * discounted because a warp only saves what ALL its lanes skip, against the
+				 * ~20 instructions the test costs everywhere else */
+				struct est e = {.s = s, .straight = straight, .boxes = boxes, .bounded = bounded, .nb = nb, .all = all};
+				double inside = 0;
+				e.reached = calloc(nb, sizeof *e.reached);
+				e.fires = calloc(nb, sizeof *e.fires);
+				est_march(&e);
+				for (uint32_t q = 0; q < nb; q++) {
+					const double saves = 1.5 * node_cost(s, s->objects[bounded[q]]);
+					const double rate = e.reached[q] ? (double)e.fires[q] / (double)e.reached[q] : 0.0;
+					own[q] = nb >= 2 && 0.8 * rate * saves > 20.0 * (1.0 - rate) + 4.0;
+					inside += saves + (own[q] ? 20.0 : 0.0);
+				}
+				{
+					const double rate = e.points ? (double)e.all_fires / (double)e.points : 0.0;
+					wrap = 0.8 * rate * inside > 20.0 * (1.0 - rate) + 4.0;
+				}
+				free(e.reached);
+				free(e.fires);
+			}
+			if (wrap) {
+				sb_printf(&body, "\t// none of the %u bounded objects can win: dist >= dbox(p) - M >= best\n\tif (!", nb);
+				emit_box_test(&g, all, two);
+				sb_printf(&body, ") {\n");
+			}
+			for (uint32_t q = 0; q < nb; q++) {
+				const uint32_t k = bounded[q];
+				emit_straight_object(&body, &g, k, sigs[k], two, 1, own[q] ? boxes[k] : NULL, wrap ? "\t\t" : "\t");
+			}
+			if (wrap)
+				sb_printf(&body, "\t}\n");
+			free(own);
+		}
+		free(straight);
+		free(boxes);
+		free(bounded);
+	}
 	for (int pass = 0; pass < 2; pass++)
 	for (uint32_t i = 0; i < s->n_objects;) {
 		uint32_t j = i + 1;
 		while (j < s->n_objects && strcmp(sigs[j], sigs[i]) == 0)
 			j++;
 		const int is_loop = (int)(j - i) >= loop_threshold;
-		/* pass 0: what comes first; pass 1: the rest */
-		const int now = prune ? (pass == 0 ? !is_loop : is_loop) : (pass == 0);
+		/* without pruning: everything in file order (pass 0); with it the straight-line
+		 * objects are already out (above) and pass 1 adds the loops */
+		const int now = prune ? (pass == 1 && is_loop) : (pass == 0);
 		if (!now) {
 			i = j;
 			continue;
@@ -724,22 +992,8 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				free(rowof);
 			}
 		} else {
-			for (uint32_t k = i; k < j; k++) {
-				g.indent = "\t\t";
-				sb_printf(&body, "\t{ // object %u: %s\n", k + 1, sigs[k]);
-				g.tmp = 0;
-				int t = emit_node(&g, s->objects[k]);
-				if (two)
-					sb_printf(&body,
-					          "\t\tconst float a_ = lol_lo(t%d), b_ = lol_hi(t%d);\n"
-					          "\t\tif (a_ < bestA) {\n\t\t\tbestA = a_;\n\t\t\tbidA = %uu;\n\t\t}\n"
-					          "\t\tif (b_ < bestB) {\n\t\t\tbestB = b_;\n\t\t\tbidB = %uu;\n\t\t}\n\t}\n",
-					          t, t, k + 1, k + 1);
-				else
-					sb_printf(&body,
-					          "\t\tif (t%d < best) {\n\t\t\tbest = t%d;\n\t\t\tbid = %uu;\n\t\t}\n\t}\n",
-					          t, t, k + 1);
-			}
+			for (uint32_t k = i; k < j; k++)
+				emit_straight_object(&body, &g, k, sigs[k], two, 0, NULL, "\t");
 		}
 		i = j;
 	}
@@ -1101,7 +1355,11 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 			return NULL;
 		}
 		/* min_blocks caps the registers; measured best for variant 3: 5 CTAs of 128 */
-		const int min_blocks = o.min_blocks > 0 ? o.min_blocks : (variant == 3 && threads == 128 ? 5 : 0);
+		/* variant 1: four CTAs of 256 (64 registers) -- without the cap ptxas takes 68 on
+		 * scene4 and a quarter of the warps is gone (measured 2.39 vs 2.30 ms) */
+		const int min_blocks = o.min_blocks > 0 ? o.min_blocks
+		                       : (variant == 3 && threads == 128) ? 5
+		                       : (variant == 1 && threads == 256) ? 4 : 0;
 		sb_printf(&out, "#define LOL_THREADS %d\n", threads);
 		if (min_blocks)
 			sb_printf(&out, "#define LOL_LAUNCH_BOUNDS __launch_bounds__(%d, %d)\n", threads, min_blocks);
