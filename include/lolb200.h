@@ -179,9 +179,12 @@ typedef struct lolb200_options {
 	                            the IEEE forms; results are bit-identical.
 	                            1 = where it pays (>= 3 spheres or a smooth
 	                            union), 2 = always, 0 = never                   */
-	int32_t prune_bounds;    /* 1: inside table loops an object is skipped when a
-	                            conservative bounding ball proves it cannot
-	                            beat the running minimum (exact)     */
+	int32_t prune_bounds;    /* 1: an object (or a group of them) is skipped when
+	                            its bounding box proves it cannot beat the
+	                            running minimum (exact): always
+	                            in table loops, in straight-line code where a
+	                            sampled estimate says the test pays; 2: every
+	                            straight-line test on; 0: off                   */
 	int32_t block_threads;   /* tuning: threads per CTA (multiple of 32);
 	                            0 = the variant's default                       */
 	int32_t min_blocks;      /* tuning: __launch_bounds__ second argument (caps

@@ -737,6 +737,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 	 * and tighten `best`, which is what the loops' bounding-ball test compares
 	 * against); the update rule of a loop then breaks ties by object id, so the
 	 * result is the reference's "first of equal distances" whatever the order. */
+	int straight_in_file_order = !prune;
 	if (prune) {
 		/* Straight-line objects, reordered: first the ones without a box (planes: one
 		 * subtraction, and they give `best` a finite value), then the bounded ones --
@@ -765,8 +766,18 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			if (isfinite(boxes[k][3]) && isfinite(boxes[k][4]) && isfinite(boxes[k][5])) {
 				bounded[nb++] = k;
 				total += node_cost(s, s->objects[k]);
-			} else
-				emit_straight_object(&body, &g, k, sigs[k], two, 0, NULL, "\t");
+			}
+		}
+		struct sb reordered = {0}; /* kept only if some test is switched on */
+		struct sb* const real_body = g.out;
+		int any_test = 0;
+		g.out = &reordered;
+		for (uint32_t k = 0; k < no; k++) {
+			int is_b = 0;
+			for (uint32_t q = 0; q < nb; q++)
+				is_b |= bounded[q] == k;
+			if (straight[k] && !is_b)
+				emit_straight_object(&reordered, &g, k, sigs[k], two, 0, NULL, "\t");
 		}
 		if (nb) {
 			float all[LOL_BOUND_SLOTS];
@@ -782,32 +793,52 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				e.reached = calloc(nb, sizeof *e.reached);
 				e.fires = calloc(nb, sizeof *e.fires);
 				est_march(&e);
+				/* model (calibrated on B200 against the four example scenes): a test is 24
+				 * instructions, reordering costs a tie-aware update (3) per bounded object, and
+				 * only 70 % of what single lanes could skip is skipped by whole warps */
 				for (uint32_t q = 0; q < nb; q++) {
-					const double saves = 1.5 * node_cost(s, s->objects[bounded[q]]);
+					/* instructions per FLOP of the convention: the IEEE forms carry their special-case code */
+					const double saves = (fast ? 1.5 : 2.3) * node_cost(s, s->objects[bounded[q]]);
 					const double rate = e.reached[q] ? (double)e.fires[q] / (double)e.reached[q] : 0.0;
-					own[q] = nb >= 2 && 0.8 * rate * saves > 20.0 * (1.0 - rate) + 4.0;
-					inside += saves + (own[q] ? 20.0 : 0.0);
+					own[q] = nb >= 2 && (prune >= 2 ? node_cost(s, s->objects[bounded[q]]) >= LOL_TEST_PAYS
+					                               : 0.7 * rate * saves > 24.0 + 3.0); /* the test is paid on every evaluation */
+					inside += saves + (own[q] ? 24.0 : 0.0);
+					if (getenv("LOLB200_DEBUG_EST"))
+						fprintf(stderr, "lolb200 estimate: object %u: own test fires %.1f %% (saves %.0f) -> %s\n",
+						        bounded[q] + 1, rate * 100, saves, own[q] ? "on" : "off");
 				}
 				{
 					const double rate = e.points ? (double)e.all_fires / (double)e.points : 0.0;
-					wrap = 0.8 * rate * inside > 20.0 * (1.0 - rate) + 4.0;
+					wrap = prune >= 2 || 0.7 * rate * inside > 24.0 + 3.0 * nb;
+					if (getenv("LOLB200_DEBUG_EST"))
+						fprintf(stderr, "lolb200 estimate: %lu points, the box around all %u fires %.1f %% (saves %.0f) -> %s\n",
+						        e.points, nb, rate * 100, inside, wrap ? "on" : "off");
 				}
 				free(e.reached);
 				free(e.fires);
 			}
 			if (wrap) {
-				sb_printf(&body, "\t// none of the %u bounded objects can win: dist >= dbox(p) - M >= best\n\tif (!", nb);
+				sb_printf(&reordered, "\t// none of the %u bounded objects can win: dist >= dbox(p) - M >= best\n\tif (!", nb);
 				emit_box_test(&g, all, two);
-				sb_printf(&body, ") {\n");
+				sb_printf(&reordered, ") {\n");
 			}
 			for (uint32_t q = 0; q < nb; q++) {
 				const uint32_t k = bounded[q];
-				emit_straight_object(&body, &g, k, sigs[k], two, 1, own[q] ? boxes[k] : NULL, wrap ? "\t\t" : "\t");
+				emit_straight_object(&reordered, &g, k, sigs[k], two, 1, own[q] ? boxes[k] : NULL, wrap ? "\t\t" : "\t");
+				any_test |= own[q];
 			}
 			if (wrap)
-				sb_printf(&body, "\t}\n");
+				sb_printf(&reordered, "\t}\n");
+			any_test |= wrap;
 			free(own);
 		}
+		g.out = real_body;
+		if (any_test)
+			sb_putn(&body, reordered.p, reordered.len);
+		else
+			straight_in_file_order = 1; /* nothing pays: the plain code, no reordering, no tie rule */
+		free(reordered.p);
+
 		free(straight);
 		free(boxes);
 		free(bounded);
@@ -820,7 +851,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		const int is_loop = (int)(j - i) >= loop_threshold;
 		/* without pruning: everything in file order (pass 0); with it the straight-line
 		 * objects are already out (above) and pass 1 adds the loops */
-		const int now = prune ? (pass == 1 && is_loop) : (pass == 0);
+		const int now = prune ? (pass == 0 ? (!is_loop && straight_in_file_order) : is_loop) : (pass == 0);
 		if (!now) {
 			i = j;
 			continue;
@@ -1385,7 +1416,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
-	         o.prune_bounds != 0, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */);
+	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

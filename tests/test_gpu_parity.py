@@ -380,3 +380,22 @@ def test_pruned_hinted_loops_equal_brute_force(csg):
         assert np.array_equal(brute["dist"].view(np.uint32), fast["dist"].view(np.uint32)), variant
         fast["renderer"].close()
     brute["renderer"].close()
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_straight_line_box_tests_do_not_change_the_frame(name, scenes_dir):
+    """Every straight-line box test forced on (prune_bounds=2) against none (0): the same
+    frame, distances, ids and step counts at 1920x1080, and the oracle's frame."""
+    import loltracer_b200 as lb
+
+    w, h = 1920, 1080
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    off = _render(lb, scene, w, h, options=lb.Options.default(prune_bounds=0))
+    for variant in (1, 3):
+        on = _render(lb, scene, w, h, options=lb.Options.default(prune_bounds=2, variant=variant, guarded_fastpath=2))
+        for key in ("rgba", "id", "nprimary", "nshadow"):
+            assert np.array_equal(off[key], on[key]), (variant, key)
+        assert np.array_equal(off["dist"].view(np.uint32), on["dist"].view(np.uint32)), variant
+        on["renderer"].close()
+    _check(off, ol.port_render(scene, w, h))
+    off["renderer"].close()

@@ -194,3 +194,44 @@ def test_cubin_cache(scenes_dir, tmp_path, monkeypatch):
     files[0].write_bytes(b"not a cubin")
     assert lb.compile_cubin(src) == first and files[0].read_bytes() == first
     assert not list(tmp_path.glob("*.tmp"))
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("variant", [1, 3])
+def test_straight_line_box_tests_are_exact_on_cpu(name, variant, scenes_dir, tmp_path):
+    """prune_bounds=2 switches every straight-line box test on (planes first, the bounded
+    objects behind the box around them and their own boxes, tie-aware updates): the same
+    distance and id as the oracle at every point, inside the boxes and far outside them."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, name, scenes_dir)
+    src = lb.lower_cuda(scene, lb.Options.default(variant=variant, prune_bounds=2, guarded_fastpath=2))
+    assert src.split("//@@SCENE@@")[0].count("lol_box_skips(x, y, z") + src.count("lol_box_skips2(x, y, z") >= 2
+    L = cpu_sdf(tmp_path, src, f"{name}box{variant}")
+    rng = np.random.default_rng(13)
+    pts = np.concatenate([rng.uniform(-40, 40, (2000, 3)), rng.normal(0, 3, (2000, 3)) + [0, 1, -6],
+                          rng.uniform(-15, 15, (2000, 3)) * [1, 0.02, 1] + [0, -0.9, -5]]).astype(np.float32)
+    d = np.zeros(len(pts), np.float32)
+    ids = np.zeros(len(pts), np.uint32)
+    fn = L.eval2 if variant == 3 else L.eval
+    fn(pts.ctypes.data_as(C.c_void_p), len(pts), d.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p))
+    wd, wi = oracle_sdf(scene, pts)
+    assert np.array_equal(d.view(np.uint32), wd.view(np.uint32))
+    assert np.array_equal(ids, wi)
+
+
+def test_box_tests_are_switched_on_where_they_pay(scenes_dir):
+    """The sampled estimate (lol_lower.c: est_march): scene4's blob is skipped in about a
+    third of all evaluations -> its test is on; scene3's blob fills the view -> off, and the
+    code is then the plain file-order code (no reordering, no tie rule)."""
+    import loltracer_b200 as lb
+
+    def sdf_text(name, **kw):
+        src = lb.lower_cuda(lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol")), lb.Options.default(**kw))
+        body = src[src.index("lol_sdf(const float x"):]
+        return body[:body.index("//@@SCENE@@")]
+
+    assert sdf_text("scene4").count("lol_box_skips(") == 1
+    assert sdf_text("scene3").count("lol_box_skips(") == 0 and "== best" not in sdf_text("scene3")
+    assert sdf_text("scene3") == sdf_text("scene3", prune_bounds=0)
+    assert sdf_text("scene3", prune_bounds=2).count("lol_box_skips(") == 1
