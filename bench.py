@@ -536,6 +536,8 @@ def main():
     exec_flops = flops_model(f_sdf, n_lights, cnt["pixels"], cnt["primary_evals"], cnt["normal_evals"],
                              cnt["shadow_evals"], cnt["normal_evals"] // 4, cnt["shadow_rays"],
                              cnt["shadow_rays_culled"])
+    # objects that a box test skipped inside an evaluation were not executed
+    exec_flops -= cnt.get("skipped_flops", 0)
     if world > 1:
         t = torch.tensor([exec_flops], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the slowest rank bounds the frame

@@ -341,7 +341,7 @@ class Renderer:
         out = (C.c_uint64 * 8)()
         _check(lib().lolb200_read_counters(self._h, C.byref(out)))
         names = ("primary_evals", "normal_evals", "shadow_evals", "pixels", "hit_pixels",
-                 "shadow_rays", "shadow_rays_culled")
+                 "shadow_rays", "shadow_rays_culled", "skipped_flops")
         return dict(zip(names, (int(x) for x in out)))
 
 

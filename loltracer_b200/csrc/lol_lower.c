@@ -637,7 +637,8 @@ static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, co
 		sb_printf(body, "%sif (t%d < best) {\n%s\tbest = t%d;\n%s\tbid = %uu;\n%s}\n", ind, t, ind, t, ind,
 		          k + 1, ind);
 	if (own_box)
-		sb_printf(body, "%s\t}\n", tabs);
+		sb_printf(body, "%s\t} else\n%s\t\tlol_count_skip(%uu);\n", tabs, tabs,
+		          (node_cost(g->s, g->s->objects[k]) + 1u) * (two ? 2u : 1u));
 	sb_printf(body, "%s}\n", tabs);
 }
 
@@ -828,7 +829,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				any_test |= own[q];
 			}
 			if (wrap)
-				sb_printf(&reordered, "\t}\n");
+				sb_printf(&reordered, "\t} else\n\t\tlol_count_skip(%uu);\n", (total + nb) * (two ? 2u : 1u));
 			any_test |= wrap;
 			free(own);
 		}
@@ -972,10 +973,12 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\t\t// the whole group: dist(any member, p) >= dbox(p) - M >= best: none can win%s\n"
 						          "\t\t\tconst lol_u32* gc = lol_run%d_groups + g * %d;\n"
 						          "\t\t\tif (lol_box_skips%s(x, y, z, LOL_TF(gc[0]), LOL_TF(gc[1]), LOL_TF(gc[2]), LOL_TF(gc[3]), "
-						          "LOL_TF(gc[4]), LOL_TF(gc[5]), LOL_TF(gc[6]), %s))\n\t\t\t\tcontinue;\n\t\t}\n",
+						          "LOL_TF(gc[4]), LOL_TF(gc[5]), LOL_TF(gc[6]), %s)) {\n"
+						          "\t\t\t\tlol_count_skip((lol_u32)(last - first) * %uu);\n\t\t\t\tcontinue;\n\t\t\t}\n\t\t}\n",
 						          two ? "\n\t\t\t// (two rays: skipped only when NEITHER can win; evaluating an object one ray could\n"
 						                "\t\t\t// have skipped does not change that ray's result)" : "",
-						          run_no, LOL_BOUND_SLOTS, sfx, best_args);
+						          run_no, LOL_BOUND_SLOTS, sfx, best_args,
+						          (node_cost(s, s->objects[i]) + 1u) * (two ? 2u : 1u));
 						sb_printf(&body, "#pragma unroll 1\n\t\tfor (int i = first; i < last; ++i) {\n");
 						if (use_hint && two)
 							sb_printf(&body, "\t\t\tif (g >= 0 && (i == hrowA || i == hrowB))\n\t\t\t\tcontinue;\n");
@@ -991,7 +994,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						cst(&r, boxes[order[q]][b]);
 					}
 					if (q == 0)
-						sb_printf(&body, ", %s))\n\t\t\t\tcontinue;\n\t\t\tconst lol_u32 oid = ", best_args);
+						sb_printf(&body, ", %s)) {\n\t\t\t\tlol_count_skip(%uu);\n\t\t\t\tcontinue;\n\t\t\t}\n"
+						          "\t\t\tconst lol_u32 oid = ", best_args,
+						          (node_cost(s, s->objects[i]) + 1u) * (two ? 2u : 1u));
 					cst_raw(&r, k + 1);
 					if (q == 0)
 						sb_printf(&body, ";\n");

@@ -335,7 +335,10 @@ def test_two_ray_kernel_4k_bit_identical_to_variant1(name, scenes_dir):
     for key in ("rgba", "id", "nprimary", "nshadow"):
         assert np.array_equal(a[key], b[key]), key
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
-    assert a["renderer"].read_counters() == b["renderer"].read_counters()
+    ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
+    # what a box test skipped differs by design: a pair skips only when both rays can
+    assert {k: v for k, v in ca.items() if k != "skipped_flops"} == {k: v for k, v in cb.items() if k != "skipped_flops"}
+    assert cb["skipped_flops"] <= ca["skipped_flops"]
 
 
 def test_host_surface_follows_a_resizing_window(scenes_dir):
