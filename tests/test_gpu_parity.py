@@ -336,9 +336,9 @@ def test_two_ray_kernel_4k_bit_identical_to_variant1(name, scenes_dir):
         assert np.array_equal(a[key], b[key]), key
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
     ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
-    # what a box test skipped differs by design: a pair skips only when both rays can
+    # what the box tests skipped differs by design: a pair skips only when both rays can, and a
+    # ray that had to evaluate its partner's objects may skip more afterwards
     assert {k: v for k, v in ca.items() if k != "skipped_flops"} == {k: v for k, v in cb.items() if k != "skipped_flops"}
-    assert cb["skipped_flops"] <= ca["skipped_flops"]
 
 
 def test_host_surface_follows_a_resizing_window(scenes_dir):
