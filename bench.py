@@ -237,6 +237,20 @@ def ncu_dram_traffic(args, w, h, world):
         return None
 
 
+def ncu_issue_utilisation(args, w, h, world):
+    """smsp__issue_active % of the same workload from the committed ncu capture: the kernel is bound by
+    instruction issue (scalar FP32 that cannot fuse in exact mode), which is what FLOP fractions miss."""
+    if world != 1 or args.scene != "scene4" or (w, h) != (3840, 2160) or args.workload != "frame":
+        return None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r01_v1_boxtest_scene4_4k.txt")):
+            if "SM issue-slot utilisation" in line:
+                return float(line.split("%")[1].split()[0]) / 100.0
+    except Exception:
+        pass
+    return None
+
+
 def flops_model(f_sdf, n_lights, pixels, primary, normal, shadow, shaded, rays_marched, rays_culled):
     """SURVEY.md 8d convention: F = E*F_sdf + 9*n_primary + 12*n_shadow + 56 (normal
     assembly, per shaded pixel) + 95 per light shaded (+20 for a culled one: L-p,
@@ -558,6 +572,7 @@ def main():
         "frac_of_nominal": achieved_tf / FP32_NOMINAL_TFLOPS,
         "flop_per_launch_executed": exec_flops, "kernel_ms": kernel_ms,
         "traffic": ncu_dram_traffic(args, w, h, world),
+        "issue_slot_utilisation_ncu": ncu_issue_utilisation(args, w, h, world),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one lol_render launch from the committed "
                         "ncu --set full capture (profiles/); the 33 MB frame stays in the 126 MB L2, so DRAM sees "
                         "only KBs -- algorithmic HBM bytes are 4 per pixel",
@@ -614,6 +629,9 @@ def main():
                                 totals["shadow"] * scale, w * h, w * h * n_lights, 0)
         roofline["achieved_reference_work"] = ref_flops / (kernel_ms * 1e-3) / 1e12
         roofline["flop_per_launch_reference"] = ref_flops
+        # the reference's own work for this frame per second of GPU time, against the same peak: what
+        # the exact skips and box tests buy on top of the hardware rate `frac`
+        roofline["frac_reference_work"] = roofline["achieved_reference_work"] / peak_tf
         # The reference's second CPU renderer, the DynASM tracing JIT, cannot be built in
         # this image (no Lua for the .dasc preprocessor).  Its stand-in: the same lowering's
         # straight-line distance code with baked constants, compiled by g++ and driven by the
