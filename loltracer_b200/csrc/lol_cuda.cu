@@ -93,6 +93,20 @@ struct lolb200_renderer {
 
 /* ------------------------------------------------------------------ NVRTC -- */
 
+/* written under a private name and renamed, so a concurrent reader (another rank
+ * preparing the same scene) never sees half a file */
+static void write_cache_file(const std::string& path, const void* image, size_t n) {
+	char tmp[4200];
+	snprintf(tmp, sizeof tmp, "%s.%ld.tmp", path.c_str(), (long)getpid());
+	if (FILE* f = fopen(tmp, "wb")) {
+		const bool ok = fwrite(image, 1, n, f) == n;
+		if (fclose(f) == 0 && ok)
+			rename(tmp, path.c_str());
+		else
+			remove(tmp);
+	}
+}
+
 extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, void** image,
                                      size_t* image_size, char** log) {
 	lolb200_options opt;
@@ -125,6 +139,15 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 			prog_name = path;
 		}
 	}
+	/* In-process memo: a group of N devices prepares the same program N times
+	 * (lolb200_group_create) -- NVRTC runs once.  Keyed by the whole program text. */
+	struct Memo {
+		std::string src;
+		int arith;
+		std::vector<char> image;
+	};
+	static std::mutex memo_mu;
+	static std::vector<Memo> memo; /* the last few programs */
 	/* LOLB200_CACHE_DIR=<dir>: compiled programs are kept as <dir>/lol-<key>.cubin,
 	 * key = two 64-bit FNV-1a hashes over the program text, the arithmetic mode, the
 	 * NVRTC version and the target.  A hit skips NVRTC (0.4-1.1 s per scene): the
@@ -163,6 +186,18 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 				free(buf); /* truncated or foreign file: recompile and replace it */
 			}
 		}
+	}
+	if (!getenv("LOLB200_DUMP_DIR")) {
+		std::lock_guard<std::mutex> lock(memo_mu);
+		for (const Memo& m : memo)
+			if (m.arith == opt.arith && m.src == src) {
+				*image = malloc(m.image.size());
+				memcpy(*image, m.image.data(), m.image.size());
+				*image_size = m.image.size();
+				if (!cache_path.empty()) /* no (valid) file yet: leave one for the next process */
+					write_cache_file(cache_path, *image, *image_size);
+				return LOLB200_OK;
+			}
 	}
 	nvrtcProgram prog;
 	nvrtcResult r = nvrtcCreateProgram(&prog, src, prog_name.c_str(), 0, nullptr, nullptr);
@@ -212,19 +247,14 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 	nvrtcGetCUBIN(prog, (char*)*image);
 	*image_size = n;
 	nvrtcDestroyProgram(&prog);
-	if (!cache_path.empty()) {
-		/* written under a private name and renamed, so a concurrent reader (another
-		 * rank preparing the same scene) never sees half a file */
-		char tmp[4200];
-		snprintf(tmp, sizeof tmp, "%s.%ld.tmp", cache_path.c_str(), (long)getpid());
-		if (FILE* f = fopen(tmp, "wb")) {
-			const bool ok = fwrite(*image, 1, n, f) == n;
-			if (fclose(f) == 0 && ok)
-				rename(tmp, cache_path.c_str());
-			else
-				remove(tmp);
-		}
+	if (!getenv("LOLB200_DUMP_DIR")) {
+		std::lock_guard<std::mutex> lock(memo_mu);
+		if (memo.size() >= 4)
+			memo.erase(memo.begin());
+		memo.push_back(Memo{src, opt.arith, std::vector<char>((char*)*image, (char*)*image + n)});
 	}
+	if (!cache_path.empty())
+		write_cache_file(cache_path, *image, n);
 	return LOLB200_OK;
 }
 
