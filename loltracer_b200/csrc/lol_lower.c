@@ -642,6 +642,14 @@ static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, co
 	sb_printf(body, "%s}\n", tabs);
 }
 
+/* The decisions of the sampled estimate, kept for the other distance functions of
+ * the same program (reference form, guarded form, two-ray form): one march each for
+ * the IEEE and the guarded cost model instead of one per function. */
+struct est_memo {
+	int valid[2], wrap[2];
+	unsigned char* own[2];
+};
+
 /* ---- the constant tables of table loops: ONE array of words ---------------------
  * Every table (rows, group boxes, id -> row) is a range of lol_tables[]; its name
  * is a macro `(LOL_TAB + offset)`.  LOL_TAB is the array itself (__constant__, or
@@ -683,7 +691,8 @@ static void tab_u32(struct tabs* T, uint32_t v) {
  * hands the whole evaluation to `fallback` when its one range check fails. */
 static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_scene* s,
                         int loop_threshold, const char* name, const char* attrs, int fast,
-                        int div_ok, const char* fallback, int prune, int two, int smem_ok) {
+                        int div_ok, const char* fallback, int prune, int two, int smem_ok,
+                        struct est_memo* memo) {
 	struct sb body = {0};
 	struct tabs tables = {{0}, {0}, 0};
 	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok, .two = two};
@@ -785,7 +794,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			unsigned char* own = calloc(nb, 1);
 			int wrap = 0;
 			group_box(boxes, bounded, nb, all);
-			if (total >= LOL_TEST_PAYS) {
+			if (total >= LOL_TEST_PAYS && memo->valid[fast != 0]) {
+				wrap = memo->wrap[fast != 0];
+				memcpy(own, memo->own[fast != 0], nb);
+			} else if (total >= LOL_TEST_PAYS) {
 				/* instructions saved where a test fires (about 1.5 per FLOP of the convention),
 				 * discounted because a warp only saves what ALL its lanes skip, against the
 				 * ~20 instructions the test costs everywhere else */
@@ -817,6 +829,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				}
 				free(e.reached);
 				free(e.fires);
+				memo->valid[fast != 0] = 1;
+				memo->wrap[fast != 0] = wrap;
+				memo->own[fast != 0] = malloc(nb);
+				memcpy(memo->own[fast != 0], own, nb);
 			}
 			if (wrap) {
 				sb_printf(&reordered, "\t// none of the %u bounded objects can win: dist >= dbox(p) - M >= best\n\tif (!", nb);
@@ -1189,30 +1205,33 @@ static int guard_pays(const lolb200_scene* s) {
 static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
                      int prune, int two, int smem_ok) {
 	struct sb tables = {0};
+	struct est_memo memo = {{0, 0}, {0, 0}, {NULL, NULL}};
 	if (guarded == 1 && !guard_pays(s) && !two)
 		guarded = 0;
 	if (guarded && constants_in_range(s)) {
 		struct sb ref = {0};
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
-		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok);
+		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok, &memo);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
 		emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf", "__forceinline__", 1, div_ok,
-		            "lol_sdf_ref", prune, 0, smem_ok);
+		            "lol_sdf_ref", prune, 0, smem_ok, &memo);
 		if (two)
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf2", "__forceinline__", 1, div_ok,
-			            "lol_sdf_ref", prune, 1, smem_ok);
+			            "lol_sdf_ref", prune, 1, smem_ok, &memo);
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
 		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
-		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok);
+		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
 	}
 	free(tables.p);
+	free(memo.own[0]);
+	free(memo.own[1]);
 }
 
 /* ----------------------------------------------------- exact-skip conditions */
