@@ -743,10 +743,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "\tfloat lo = LOL_COORD_MAX - fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));\n");
 
 	/* Segments: maximal runs of same-shaped neighbours.  Long runs become table
-	 * loops.  With pruning the short segments are evaluated FIRST (they are cheap
-	 * and tighten `best`, which is what the loops' bounding-ball test compares
-	 * against); the update rule of a loop then breaks ties by object id, so the
-	 * result is the reference's "first of equal distances" whatever the order. */
+	 * loops.  With pruning the straight-line objects are evaluated FIRST (they
+	 * tighten `best`, which is what every box test compares against); the update
+	 * rules then break ties by object id, so the result is the reference's "first of
+	 * equal distances" whatever the order. */
 	int straight_in_file_order = !prune;
 	if (prune) {
 		/* Straight-line objects, reordered: first the ones without a box (planes: one

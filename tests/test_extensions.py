@@ -79,7 +79,7 @@ def test_lowered_extension_nodes_equal_oracle_on_cpu(kind, variant, tmp_path):
 
 def test_csg_synthetic_scene_lowers_to_one_table_loop(tmp_path):
     """The 1024-primitive CSG scene: one loop over 128 rows of U(U(I,D),U(I,D)), pruned by
-    bounding balls (intersection: the smaller child ball; difference: a's ball)."""
+    bounding boxes (intersection: the smaller child box; difference: a's box)."""
     import loltracer_b200 as lb
     from loltracer_b200 import scenegen
 

@@ -301,7 +301,7 @@ def test_variant2_shards_and_small_chunks(variant, world, scenes_dir):
 
 @pytest.mark.parametrize("name", ["scene", "scene2", "synthetic"])
 def test_table_loops_and_pruning_are_exact(name, scenes_dir):
-    """Forced table loops (threshold 2) with bounding-ball pruning and hoisted short
+    """Forced table loops (threshold 2) with box pruning, groups, hints and hoisted short
     segments vs fully unrolled code: identical distance, id and pixels."""
     import loltracer_b200 as lb
     from loltracer_b200 import scenegen

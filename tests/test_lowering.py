@@ -37,7 +37,7 @@ def _scene(lb, name, scenes_dir):
 @pytest.mark.parametrize("loops", [0, 2])
 def test_generated_sdf_equals_oracle_on_cpu(name, loops, scenes_dir, tmp_path):
     """Each primitive and smooth union as the lowering emits it == sdf.h / float.h.
-    loops=2 forces table loops (with bounding-ball pruning and hoisted short
+    loops=2 forces table loops (with box pruning, groups, hints and hoisted short
     segments) onto the small scenes too."""
     import loltracer_b200 as lb
 
