@@ -195,18 +195,16 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 	case LOLB200_OBJ_BOX: /* sdRoundBox, sdf.h:18-22 */
 		me = g->tmp++;
 		if (g->two) {
-			/* no two-wide abs/max: the box runs per half on the packed coordinates */
+			/* no two-wide abs/max: the box runs per half on the packed coordinates.  The
+			 * constants are read in the scalar form's order (centre, extent per axis, then
+			 * the radius): in a table loop both forms read the same row. */
 			sb_printf(g->out, "%sconst lol_f2 t%d = lol_roundbox2(", g->indent, me);
-			coord_minus(g, "x", o->point[0]);
-			sb_printf(g->out, ", ");
-			coord_minus(g, "y", o->point[1]);
-			sb_printf(g->out, ", ");
-			coord_minus(g, "z", o->point[2]);
 			for (int k = 0; k < 3; k++) {
+				coord_minus(g, k == 0 ? "x" : k == 1 ? "y" : "z", o->point[k]);
 				sb_printf(g->out, ", ");
 				cst(g, o->point2[k]);
+				sb_printf(g->out, ", ");
 			}
-			sb_printf(g->out, ", ");
 			cst(g, o->radius);
 			sb_printf(g->out, ");\n");
 			return me;
