@@ -58,8 +58,28 @@ def _material(text, m):
     return f"{head}{{ material = #{m},{rest}"
 
 
-def random_scene(seed, extensions):
+def random_head(rng):
+    """Materials, camera and lights: material 0 is usually black (the miss shortcut is licensed)
+    but not always; shininess is sometimes negative (the back-face cull is then not licensed);
+    zero to three lights."""
+    m0 = "(0,0,0)" if rng.random() < 0.7 else "(0.05,0.02,0.03)"
+    shin = 8 if rng.random() < 0.8 else -2
+    lights = "".join(
+        f"  point_light {{ point = {_vec(rng.uniform(-8, 8, 3) + [0, 6, 0])}, diffuse_intensity = {_vec(rng.uniform(0.5, 4, 3))}, "
+        f"specular_intensity = {_vec(rng.uniform(0.5, 4, 3))} }},\n" for _ in range(int(rng.integers(0, 4))))
+    cam = rng.uniform(-2, 2, 3) + [0, 2, 6]
+    return f"""materials {{
+  {{ shininess = 0, diffuse = {m0}, specular = (0,0,0), ambient = {m0} }},
+  {{ shininess = {shin}, diffuse = (0.3,0.2,0.1), specular = (0.1,0.1,0.1), ambient = (0.3,0.2,0.1) }},
+  {{ shininess = 2, diffuse = (0.1,0.2,0.3), specular = (0.2,0.1,0.1), ambient = (0.1,0.2,0.3) }} }}
+scene {{ ambient {{ color = (0.05, 0.05, 0.05) }},
+  camera {{ point = {_vec(cam)}, direction = {_vec([-cam[0] * 0.1, -0.2, -1])}, fov = {int(rng.choice([60, 90, 120]))} }},
+{lights}"""
+
+
+def random_scene(seed, extensions, fixed_head=True):
     rng = np.random.default_rng(seed)
+    head = HEAD if fixed_head else random_head(np.random.default_rng(seed + 7))
     objs = []
     for _ in range(rng.integers(1, 7)):
         objs.append(_material(_tree(rng, int(rng.integers(0, 4)), extensions), int(rng.integers(1, 3))))
@@ -77,7 +97,7 @@ def random_scene(seed, extensions):
             objs.append(_material(text, 1 + i % 2))
     if rng.random() < 0.8:
         objs.insert(int(rng.integers(0, len(objs) + 1)), f"plane {{ y = {_num(rng.uniform(-3, 0))}, material = #2 }}")
-    return HEAD + ",\n".join("  " + o for o in objs) + " }\n"
+    return head + ",\n".join("  " + o for o in objs) + " }\n"
 
 
 def oracle_sdf(scene, pts):
@@ -126,7 +146,7 @@ def test_random_scenes_render_like_the_oracle(seed, extensions):
     import loltracer_b200 as lb
     from test_gpu_parity import _check, _render
 
-    scene = lb.Scene.from_string(random_scene(seed + (100 if extensions else 0), extensions))
+    scene = lb.Scene.from_string(random_scene(seed + (100 if extensions else 0), extensions, fixed_head=False))
     w, h = 200, 112
     want = ol.port_render(scene, w, h)
     for variant, loops, prune in [(1, 2, 2), (3, 2, 2), (1, 0, 1)]:
