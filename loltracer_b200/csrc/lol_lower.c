@@ -507,7 +507,7 @@ static int est_box_skips(const float p[3], const float b[7], float best) {
 
 struct est {
 	const lolb200_scene* s;
-	const unsigned char* straight; /* per object: evaluated in straight-line code */
+	const unsigned char* straight; /* per object: 1 = straight-line code, 2 = straight-line and bounded */
 	float (*boxes)[LOL_BOUND_SLOTS];
 	const uint32_t* bounded;       /* the bounded straight-line objects */
 	uint32_t nb;
@@ -519,13 +519,9 @@ struct est {
 static float est_sdf(struct est* e, const float p[3]) {
 	const lolb200_scene* s = e->s;
 	float best = INFINITY;
-	for (uint32_t k = 0; k < s->n_objects; k++) { /* the objects without a box come first */
-		int is_bounded = 0;
-		for (uint32_t q = 0; q < e->nb; q++)
-			is_bounded |= e->bounded[q] == k;
-		if (e->straight[k] && !is_bounded)
+	for (uint32_t k = 0; k < s->n_objects; k++) /* the objects without a box come first */
+		if (e->straight[k] == 1)
 			best = fminf(best, est_node(s, s->objects[k], p));
-	}
 	e->points++;
 	if (est_box_skips(p, e->all, best))
 		e->all_fires++;
@@ -549,7 +545,12 @@ static void est_march(struct est* e) {
 	lolb200_camera_basis_compute(&s->camera, w, h, &cb);
 	for (int y = 0; y < h; y++)
 		for (int x = 0; x < w; x++) {
-			const float vx = ((float)x + .5f) / (float)w * 2.f - 1.f, vy = 1.f - ((float)y + .5f) / (float)h * 2.f;
+			/* a bounded effort: about 4e7 node evaluations (a fraction of a second), in
+			 * an order that still covers the frame when it is cut short */
+			if ((double)e->points * (double)s->n_nodes > 4e7)
+				return;
+			const int px = (x * 7) % w, py = (y * 5) % h; /* 7, 5 coprime to 64x36 and 24x14 */
+			const float vx = ((float)px + .5f) / (float)w * 2.f - 1.f, vy = 1.f - ((float)py + .5f) / (float)h * 2.f;
 			float rd[3], t = 0.f;
 			for (int c = 0; c < 3; c++)
 				rd[c] = cb.right[c] * (vx * cb.width) + cb.up[c] * (vy * cb.height) + cb.dir[c];
@@ -773,6 +774,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			bound_row(s, s->objects[k], boxes[k]);
 			if (isfinite(boxes[k][3]) && isfinite(boxes[k][4]) && isfinite(boxes[k][5])) {
 				bounded[nb++] = k;
+				straight[k] = 2;
 				total += node_cost(s, s->objects[k]);
 			}
 		}
@@ -780,13 +782,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		struct sb* const real_body = g.out;
 		int any_test = 0;
 		g.out = &reordered;
-		for (uint32_t k = 0; k < no; k++) {
-			int is_b = 0;
-			for (uint32_t q = 0; q < nb; q++)
-				is_b |= bounded[q] == k;
-			if (straight[k] && !is_b)
+		for (uint32_t k = 0; k < no; k++)
+			if (straight[k] == 1)
 				emit_straight_object(&reordered, &g, k, sigs[k], two, 0, NULL, "\t");
-		}
 		if (nb) {
 			float all[LOL_BOUND_SLOTS];
 			unsigned char* own = calloc(nb, 1);
