@@ -402,3 +402,29 @@ def test_straight_line_box_tests_do_not_change_the_frame(name, scenes_dir):
         on["renderer"].close()
     _check(off, ol.port_render(scene, w, h))
     off["renderer"].close()
+
+
+@pytest.mark.parametrize("name,point,direction", [
+    ("scene4", (0, 1, -6), (0, 0, -1)),          # the camera sits exactly at a sphere's centre: sqrt(0)
+    ("scene4", (-1, 0.5, -3), (0.3, 0.2, -1)),   # another centre, inside the blob
+    ("scene4", (3e19, 1, 0), (-1, 0, 0)),        # beyond 2^60: the guard's coordinate range
+    ("scene2", (0, 5, -6), (0, -1, 0)),          # straight down: cross(dir, up) = 0, a NaN camera basis
+    ("scene", (2, 2, -10), (0, 0, -1)),          # inside the round box
+])
+@pytest.mark.parametrize("variant", [1, 3])
+def test_cameras_outside_the_fast_forms_ranges(name, point, direction, variant, scenes_dir):
+    """Where the guarded fast path must fall back to the IEEE forms (and where everything is NaN)
+    the frame is still the oracle's, pixel for pixel."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    cam = lb.Camera.make(list(point), list(direction), scene.struct.camera.fov)
+    w, h = 160, 90
+    got = _render(lb, scene, w, h, camera=cam, options=lb.Options.default(variant=variant, guarded_fastpath=2))
+    want = ol.port_render(scene, w, h, camera=cam)
+    cmp = ol.compare_frames(got["rgba"], got["id"], want["rgba"], want["id"])
+    assert cmp["n_mask_off"] == 0 and cmp["max_rgb_err"] <= 1, cmp
+    assert np.array_equal(got["id"], want["id"])
+    same = (got["dist"].view(np.uint32) == want["dist"].view(np.uint32)) | (np.isnan(got["dist"]) & np.isnan(want["dist"]))
+    assert same.all()
+    got["renderer"].close()

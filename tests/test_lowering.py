@@ -235,3 +235,30 @@ def test_box_tests_are_switched_on_where_they_pay(scenes_dir):
     assert sdf_text("scene3").count("lol_box_skips(") == 0 and "== best" not in sdf_text("scene3")
     assert sdf_text("scene3") == sdf_text("scene3", prune_bounds=0)
     assert sdf_text("scene3", prune_bounds=2).count("lol_box_skips(") == 1
+
+
+@pytest.mark.parametrize("name", ["scene4", "scene", "synthetic"])
+@pytest.mark.parametrize("variant", [1, 3])
+def test_points_outside_the_guard_take_the_ieee_path(name, variant, scenes_dir, tmp_path):
+    """Exactly at a sphere's centre (squared length 0 < 2^-101), beyond 2^60, and NaN: the one
+    range guard of the fast forms must hand the evaluation to lol_sdf_ref, with the oracle's result."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, name, scenes_dir)
+    st = scene.struct
+    centres = [list(st.nodes[i].point) for i in range(st.n_nodes) if st.nodes[i].type == 3][:40]
+    pts = np.array(centres + [[3e19, 1, 0], [0, -2e30, 5], [1e-30, 1, -6], [np.nan, 0, 0], [0, np.inf, 0]] +
+                   [[c[0], c[1], c[2] + 1e-20] for c in centres[:8]], np.float32)
+    if len(pts) % 2:
+        pts = np.concatenate([pts, pts[:1]])
+    src = lb.lower_cuda(scene, lb.Options.default(variant=variant, guarded_fastpath=2))
+    assert "lol_sdf_ref(" in src
+    L = cpu_sdf(tmp_path, src, f"guard_{name}{variant}")
+    d = np.zeros(len(pts), np.float32)
+    ids = np.zeros(len(pts), np.uint32)
+    fn = L.eval2 if variant == 3 else L.eval
+    fn(pts.ctypes.data_as(C.c_void_p), len(pts), d.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p))
+    wd, wi = oracle_sdf(scene, pts)
+    same = (d.view(np.uint32) == wd.view(np.uint32)) | (np.isnan(d) & np.isnan(wd))
+    assert same.all(), (pts[~same], d[~same], wd[~same])
+    assert np.array_equal(ids, wi)
