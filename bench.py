@@ -237,6 +237,21 @@ def ncu_dram_traffic(args, w, h, world):
         return None
 
 
+def ncu_hw_flop_frac(args, w, h, world):
+    """FP32 FLOPs as the hardware counts them (ncu: fadd + fmul + 2 ffma thread-instructions per cycle, of the
+    chip's peak) for the same workload, from the committed capture: every executed FP32 instruction, including
+    the Newton steps of sqrt, the box tests and the range guards that the algorithmic model does not credit."""
+    if world != 1 or args.scene != "scene4" or (w, h) != (3840, 2160) or args.workload != "frame":
+        return None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r01_v1_boxtest_scene4_4k.txt")):
+            if "hardware FP32 FLOP/cycle" in line:
+                return float(line.split("=")[1].split("%")[0]) / 100.0
+    except Exception:
+        pass
+    return None
+
+
 def ncu_issue_utilisation(args, w, h, world):
     """smsp__issue_active % of the same workload from the committed ncu capture: the kernel is bound by
     instruction issue (scalar FP32 that cannot fuse in exact mode), which is what FLOP fractions miss."""
@@ -573,6 +588,7 @@ def main():
         "flop_per_launch_executed": exec_flops, "kernel_ms": kernel_ms,
         "traffic": ncu_dram_traffic(args, w, h, world),
         "issue_slot_utilisation_ncu": ncu_issue_utilisation(args, w, h, world),
+        "hw_fp32_frac_ncu": ncu_hw_flop_frac(args, w, h, world),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one lol_render launch from the committed "
                         "ncu --set full capture (profiles/); the 33 MB frame stays in the 126 MB L2, so DRAM sees "
                         "only KBs -- algorithmic HBM bytes are 4 per pixel",
