@@ -211,7 +211,8 @@ def run_reference(args, w, h):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "ms_per_frame_extrapolated": ms_per_step * (w * h / rays),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"{args.scene}.lol at {w}x{h}", "sample": sample},
+        "data": "synthetic", "config": {"workload": f"{args.scene}.lol at {w}x{h}, one primary ray per pixel (the frame of the b200 arm, "
+                                           f"rendered by the reference's CPU renderer)", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
