@@ -156,6 +156,33 @@ def cpu_sample(scene_name, w, h, ystride, repeats=1, force_port=False, want_tota
     return best, rays, kind, cores, totals
 
 
+def cpu_baseline_variants(scene_name, w, h):
+    """The reference's naive renderer on ONE thread, and built without optimisation (its Makefile passes no
+    -O flag, Makefile:3) on all threads: small samples of the same frame, a second or so each."""
+    import oracle_lib as ol
+
+    if not ol.have_ref() or scene_name.startswith("synthetic"):
+        return None
+    path = scene_name if os.path.exists(scene_name) else os.path.join(ROOT, "tests", "golden", "scenes", scene_name + ".lol")
+    res = {}
+    rs = ol.RefScene(path=path)
+    stride = max(1, h // 24)
+    rows = (h + stride - 1) // stride
+    ms = rs.probe(w, h, ystride=stride, threads=1)["ms"]
+    res["one_thread_O2"] = {"value": rows * w / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": 1,
+                            "sample": f"every {stride}th scanline ({rows * w} rays, {ms:.0f} ms)"}
+    if os.path.exists(ol.REF_O0_PATH):
+        r0 = ol.RefScene(path=path, lib=ol.ref(ol.REF_O0_PATH))
+        stride = max(1, h // 96)
+        rows = (h + stride - 1) // stride
+        r0.probe(w, h, ystride=stride * 4)  # warm the threads
+        ms = r0.probe(w, h, ystride=stride)["ms"]
+        res["all_threads_O0"] = {"value": rows * w / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": ol.nthreads(),
+                                 "sample": f"every {stride}th scanline ({rows * w} rays, {ms:.0f} ms), "
+                                           "gcc -O0 as the reference Makefile builds it"}
+    return res
+
+
 def cpu_jit_equivalent(scene_name, w, h, ystride):
     """JIT-equivalent CPU renderer (stand-in for tracing_jit_renderer.dasc) on the sample."""
     import tempfile
@@ -649,6 +676,11 @@ def main():
         # the reference's own work for this frame per second of GPU time, against the same peak: what
         # the exact skips and box tests buy on top of the hardware rate `frac`
         roofline["frac_reference_work"] = roofline["achieved_reference_work"] / peak_tf
+        # one thread, and the reference as its own Makefile builds it (no -O flag)
+        try:
+            out["cpu_baseline"]["variants"] = cpu_baseline_variants(args.scene, w, h)
+        except Exception as e:
+            out["cpu_baseline"]["variants"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         # The reference's second CPU renderer, the DynASM tracing JIT, cannot be built in
         # this image (no Lua for the .dasc preprocessor).  Its stand-in: the same lowering's
         # straight-line distance code with baked constants, compiled by g++ and driven by the

@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PORT_PATH = os.path.join(ROOT, "oracle", "liblol_oracle.so")
 REF_PATH = os.path.join(ROOT, "oracle", "_ref", "liblolref.so")
+REF_O0_PATH = os.path.join(ROOT, "oracle", "_ref", "liblolref_O0.so")  # as the reference Makefile builds it: no -O
 
 _port = None
 _ref = None
@@ -37,10 +38,18 @@ def have_ref() -> bool:
     return os.path.exists(REF_PATH)
 
 
-def ref():
+def ref(path=None):
+    """The compiled reference; path=REF_O0_PATH: the same sources without optimisation."""
     global _ref
+    if path is not None:
+        return _bind_ref(C.CDLL(path))
     if _ref is None:
-        L = C.CDLL(REF_PATH)
+        _ref = _bind_ref(C.CDLL(REF_PATH))
+    return _ref
+
+
+def _bind_ref(L):
+    if True:
         L.lolref_scene_load.restype = C.c_void_p
         L.lolref_scene_load.argtypes = [C.c_char_p]
         L.lolref_scene_load_string.restype = C.c_void_p
@@ -56,8 +65,7 @@ def ref():
         L.lolref_probe.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] * 3
         L.lolref_sdf.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_float),
                                  C.POINTER(C.c_uint32)]
-        _ref = L
-    return _ref
+    return L
 
 
 def nthreads() -> int:
@@ -94,25 +102,26 @@ def port_render(scene, w, h, camera=None, mode=0, y0=0, y1=None, ystride=1, thre
 class RefScene:
     """A scene held by the compiled reference (struct scene*, built by its own scene.c)."""
 
-    def __init__(self, path=None, text=None):
+    def __init__(self, path=None, text=None, lib=None):
+        self.lib = lib or ref()
         if path is not None:
-            self.ptr = ref().lolref_scene_load(os.fsencode(path))
+            self.ptr = self.lib.lolref_scene_load(os.fsencode(path))
         else:
             raw = text.encode()
-            self.ptr = ref().lolref_scene_load_string(raw, len(raw))
+            self.ptr = self.lib.lolref_scene_load_string(raw, len(raw))
         if not self.ptr:
             raise RuntimeError("reference failed to load the scene")
 
     def set_camera(self, point, direction):
         p = (C.c_float * 3)(*point)
         d = (C.c_float * 3)(*direction)
-        ref().lolref_scene_set_camera(self.ptr, C.byref(p), C.byref(d))
+        self.lib.lolref_scene_set_camera(self.ptr, C.byref(p), C.byref(d))
 
     def flatten(self):
         """The reference's structs through the backend's translation -> SceneStruct pointer."""
         from loltracer_b200.api import SceneStruct, Scene
 
-        p = ref().lolref_scene_flatten(self.ptr)
+        p = self.lib.lolref_scene_flatten(self.ptr)
         return Scene(C.cast(p, C.POINTER(SceneStruct)))
 
     def probe(self, w, h, y0=0, y1=None, ystride=1, threads=None):
@@ -120,7 +129,7 @@ class RefScene:
         dist = np.zeros((rows, w), np.float32)
         ids = np.zeros((rows, w), np.uint32)
         rgba = np.zeros((rows, w), np.uint32)
-        ms = ref().lolref_probe(self.ptr, w, h, y0, y1, ystride, threads or nthreads(),
+        ms = self.lib.lolref_probe(self.ptr, w, h, y0, y1, ystride, threads or nthreads(),
                                 dist.ctypes.data, ids.ctypes.data, rgba.ctypes.data)
         return dict(dist=dist, id=ids, rgba=rgba, ms=ms)
 
@@ -128,7 +137,7 @@ class RefScene:
         """Through the unmodified render_thread() and main.c's semaphore protocol."""
         px = np.zeros((h, w), np.uint32)
         ms = (C.c_double * frames)()
-        ref().lolref_render_protocol(self.ptr, w, h, threads or nthreads(), frames,
+        self.lib.lolref_render_protocol(self.ptr, w, h, threads or nthreads(), frames,
                                      px.ctypes.data, C.cast(ms, C.c_void_p))
         return px, list(ms)
 

@@ -167,3 +167,15 @@ def test_specialised_sdf_mode_equals_naive(name, scenes_dir, tmp_path):
         assert np.array_equal(naive[key], spec[key]), key
     assert np.array_equal(naive["dist"].view(np.uint32), spec["dist"].view(np.uint32))
     assert keep is not None
+
+
+def test_reference_built_without_optimisation_renders_the_same_frame(scenes_dir):
+    """The reference's Makefile passes no -O flag; oracle/_ref/liblolref_O0.so is that build.
+    Same frame as the -O2 build the other pins use (IEEE semantics do not depend on -O)."""
+    if not (ol.have_ref() and os.path.exists(ol.REF_O0_PATH)):
+        pytest.skip("oracle/_ref not built here")
+    path = os.path.join(scenes_dir, "scene4.lol")
+    a = ol.RefScene(path=path).probe(96, 54)
+    b = ol.RefScene(path=path, lib=ol.ref(ol.REF_O0_PATH)).probe(96, 54)
+    assert np.array_equal(a["rgba"], b["rgba"]) and np.array_equal(a["id"], b["id"])
+    assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
