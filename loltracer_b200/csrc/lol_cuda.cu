@@ -18,6 +18,8 @@
 #include <nccl.h>
 #include <nvrtc.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -89,6 +91,17 @@ struct lolb200_renderer {
 	size_t registered_bytes = 0;
 	void* registered_dev = nullptr; /* device view of the pinned surface (zero-copy) */
 	int host_mode = 0;              /* 0 copy after the kernel, 1 zero-copy stores */
+	/* longest-first chunk order (full-shard launches of lolb200_render_device) */
+	struct {
+		int w = 0, h = 0, rank = -1, world = 0;
+		lol_u32 chunk_w = 0, n_chunks = 0;
+		lol_u32 *cost = nullptr, *cost_sorted = nullptr, *ids = nullptr, *order = nullptr;
+		void* tmp = nullptr;
+		size_t tmp_bytes = 0, cap = 0;
+		unsigned frames = 0; /* launches with this geometry */
+		bool have_order = false;
+		void* stream = nullptr; /* the stream the order was produced on */
+	} lpt;
 	cudaEvent_t t_begin = nullptr, t_end = nullptr; /* the previous host frame's render time */
 	float last_render_ms = 0.f, last_copy_ms_est = 0.f;
 };
@@ -280,6 +293,11 @@ extern "C" void lolb200_renderer_destroy(lolb200_renderer* r) {
 			cudaStreamSynchronize(r->stream);
 			cudaStreamDestroy(r->stream);
 		}
+		cudaFree(r->lpt.cost);
+		cudaFree(r->lpt.cost_sorted);
+		cudaFree(r->lpt.ids);
+		cudaFree(r->lpt.order);
+		cudaFree(r->lpt.tmp);
 		if (r->t_begin)
 			cudaEventDestroy(r->t_begin);
 		if (r->t_end)
@@ -485,6 +503,71 @@ static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands
 	return min_w;
 }
 
+__global__ void lol_iota_kernel(lol_u32* v, lol_u32 n) {
+	const lol_u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		v[i] = i;
+}
+
+/* Longest-first scheduling.  The kernel records what every chunk cost (clocks); every
+ * few frames the costs are sorted (cub radix sort, descending) into the order in which
+ * the next frames pull their chunks.  The camera of a viewer moves slowly and a
+ * benchmark repeats its frame, so last frame's costs predict this frame's.  Only for
+ * launches that cover a whole shard on one stream; LOLB200_LPT=0 turns it off. */
+static bool lpt_prepare(lolb200_renderer* r, const lol_params& P, void* stream) {
+	static const bool enabled = [] {
+		const char* e = getenv("LOLB200_LPT");
+		return !(e && !strcmp(e, "0"));
+	}();
+	auto& L = r->lpt;
+	if (!enabled || P.n_chunks < 1024)
+		return false;
+	if (L.w != P.w || L.h != P.h || L.rank != P.rank || L.world != P.world || L.chunk_w != P.chunk_w ||
+	    L.n_chunks != P.n_chunks || L.stream != stream) {
+		if (L.cap < P.n_chunks) {
+			cudaFree(L.cost);
+			cudaFree(L.cost_sorted);
+			cudaFree(L.ids);
+			cudaFree(L.order);
+			cudaFree(L.tmp);
+			L.cost = L.cost_sorted = L.ids = L.order = nullptr;
+			L.tmp = nullptr;
+			L.cap = 0;
+			const size_t bytes = (size_t)P.n_chunks * sizeof(lol_u32);
+			size_t tmp_bytes = 0;
+			cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, L.cost, L.cost_sorted, L.ids, L.order,
+			                                          (int)P.n_chunks);
+			if (cudaMalloc(&L.cost, bytes) != cudaSuccess || cudaMalloc(&L.cost_sorted, bytes) != cudaSuccess ||
+			    cudaMalloc(&L.ids, bytes) != cudaSuccess || cudaMalloc(&L.order, bytes) != cudaSuccess ||
+			    cudaMalloc(&L.tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) {
+				cudaGetLastError();
+				return false;
+			}
+			L.tmp_bytes = tmp_bytes;
+			L.cap = P.n_chunks;
+		}
+		L.w = P.w, L.h = P.h, L.rank = P.rank, L.world = P.world;
+		L.chunk_w = P.chunk_w, L.n_chunks = P.n_chunks;
+		L.frames = 0;
+		L.have_order = false;
+		L.stream = stream;
+		lol_iota_kernel<<<(P.n_chunks + 255) / 256, 256, 0, (cudaStream_t)stream>>>(L.ids, P.n_chunks);
+	}
+	return true;
+}
+
+/* after the render launch: turn the recorded costs into the next frames' order */
+static void lpt_after_launch(lolb200_renderer* r, void* stream) {
+	auto& L = r->lpt;
+	const unsigned f = L.frames++;
+	if (f == 0 || f % 8 == 7) { /* after the first frame, then every eighth */
+		size_t tmp_bytes = L.tmp_bytes;
+		cub::DeviceRadixSort::SortPairsDescending(L.tmp, tmp_bytes, L.cost, L.cost_sorted, L.ids, L.order,
+		                                          (int)L.n_chunks, 0, 32, (cudaStream_t)stream);
+		L.have_order = true;
+	}
+}
+
 /* One launch over local bands [band_begin, band_begin + band_count) of the
  * rank's share (band_count = 0: all of them). */
 static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
@@ -558,6 +641,12 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 	P.stats = r->stats;
 
 	DeviceGuard g(r->device);
+	/* a whole shard in one launch: chunks are pulled longest first */
+	const bool lpt = band_begin == 0 && band_count == 0 && counter_slot == 0 && lpt_prepare(r, P, stream);
+	if (lpt) {
+		P.cost = r->lpt.cost;
+		P.order = r->lpt.have_order ? r->lpt.order : nullptr;
+	}
 	const size_t warps_needed = P.n_chunks;
 	size_t grid = (size_t)r->sm_count * r->blocks_per_sm;
 	const size_t grid_needed = (warps_needed + r->threads / 32 - 1) / (r->threads / 32);
@@ -566,6 +655,8 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 	void* args[] = {&P};
 	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3((unsigned)r->threads),
 	                          args, r->dyn_smem, (cudaStream_t)stream));
+	if (lpt)
+		lpt_after_launch(r, stream);
 	return LOLB200_OK;
 }
 

@@ -34,6 +34,8 @@ struct lol_params {
 	lol_u16* aux_primary;
 	lol_u16* aux_shadow;
 	lol_u64* stats;      // LOL_COUNTERS: 8 accumulators
+	const lol_u32* order; // optional: n-th pull from the queue -> chunk (longest first)
+	lol_u32* cost;        // optional: clocks each chunk took, by chunk
 };
 
 #define LOL_BAND_ROWS 4
