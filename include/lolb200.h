@@ -196,7 +196,15 @@ typedef struct lolb200_options {
 	                            unrolled; -1... not used; default 1             */
 	int32_t prune_group;     /* tuning: objects per group of the two-level box
 	                            pruning in table loops; 0 = default (8)         */
-	int32_t reserved[3];
+	int32_t pack_pairs;      /* exact mode with the guarded forms: two subtrees of one
+	                            shape inside an object (two spheres, two smooth
+	                            unions of spheres, ...) are evaluated as ONE packed
+	                            FP32 instruction stream (FADD2 / FMUL2 / FFMA2, one
+	                            subtree per half; each half rounds like the scalar
+	                            instruction, so results are bit-identical).
+	                            1 = where it pays (inside table loops), 2 =
+	                            everywhere, 3 = everywhere, leaves only, 0 = never */
+	int32_t reserved[2];
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

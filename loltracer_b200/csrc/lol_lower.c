@@ -83,8 +83,20 @@ static void sb_bits(struct sb* b, float f) {
 
 /* ------------------------------------------------------------ distance code */
 
-/* Where a constant comes from: an immediate, or slot j of the current row of a
- * run table (loop mode). */
+/* Where a constant comes from: an immediate, or a slot of the current row of a
+ * run table (loop mode).  A row is laid out before its code is written: the box
+ * and the object id first (cst / cst_raw, in emission order), then every node's
+ * constants in post-order (layout_object), so that the reference form, the
+ * guarded form and the packed pairs -- which read them in different orders --
+ * agree on where each one lives. */
+struct pair_plan {
+	uint32_t a, b; /* roots of two disjoint subtrees of one shape: low / high half */
+	int tmp;       /* the lol_f2 temporary that holds both results, -1 = not emitted yet */
+};
+struct pairc { /* the constant pairs of one function: (low, high) bits */
+	uint32_t (*w)[2];
+	size_t n, cap;
+};
 struct cgen {
 	const lolb200_scene* s;
 	struct sb* out;
@@ -93,35 +105,35 @@ struct cgen {
 	int fast;     /* 1: guarded fast forms (lol_sqrt_fast, lol_smin_c) */
 	int div_ok;   /* 1: every smoothness passed the constant-division proof */
 	int two;      /* 1: two rays per evaluation, packed FP32 (lol_f2, variant 3) */
+	int pack;     /* 1: same-shaped subtrees of one ray in pairs, packed FP32 (plan_pairs) */
 	float* row;
 	size_t nrow, caprow;
+	size_t* slot;        /* loop mode: first row slot of each node's constants */
+	unsigned char* stride; /* ... and the distance between its fields: 2 inside a pair (a.f, b.f adjacent) */
+	int lay_pack, lay_div_ok; /* the pairing of the GUARDED form: every form of a program reads one row layout */
+	uint32_t* pair_of;   /* per node: 0, or 1 + 2 * pair + half for the roots of a planned pair */
+	struct pair_plan* pairs;
+	size_t npairs;
+	struct pairc* pc;    /* where constant pairs of straight-line code go */
 	const char* indent;
 };
 
+static void row_push(struct cgen* g, float v) {
+	if (g->nrow == g->caprow) {
+		g->caprow = g->caprow ? g->caprow * 2 : 16;
+		g->row = realloc(g->row, g->caprow * sizeof(float));
+	}
+	g->row[g->nrow++] = v;
+}
+
+/* a constant that is not a node's (a bounding box): next slot of the row */
 static void cst(struct cgen* g, float v) {
 	if (!g->in_loop) {
 		sb_float(g->out, v);
 		return;
 	}
-	if (g->nrow == g->caprow) {
-		g->caprow = g->caprow ? g->caprow * 2 : 16;
-		g->row = realloc(g->row, g->caprow * sizeof(float));
-	}
 	sb_printf(g->out, "LOL_TF(c[%zu])", g->nrow);
-	g->row[g->nrow++] = v;
-}
-
-/* Reserves the table slot of a constant this variant of the code does not read,
- * so that the guarded and the reference function share one row layout. */
-static void cst_skip(struct cgen* g, float v) {
-	struct sb nowhere = {0};
-	struct sb* keep = g->out;
-	if (!g->in_loop)
-		return;
-	g->out = &nowhere;
-	cst(g, v);
-	g->out = keep;
-	free(nowhere.p);
+	row_push(g, v);
 }
 
 /* An integer constant (an object id): raw bits in the table, read without LOL_TF. */
@@ -131,25 +143,342 @@ static void cst_raw(struct cgen* g, uint32_t v) {
 		sb_printf(g->out, "%uu", v);
 		return;
 	}
-	if (g->nrow == g->caprow) {
-		g->caprow = g->caprow ? g->caprow * 2 : 16;
-		g->row = realloc(g->row, g->caprow * sizeof(float));
-	}
 	sb_printf(g->out, "c[%zu]", g->nrow);
 	memcpy(&f, &v, 4);
-	g->row[g->nrow++] = f;
+	row_push(g, f);
+}
+
+/* A node's constants: sphere (centre, radius), rounded box (centre and extent per
+ * axis, radius), plane (y), smooth union (k, RN(1/k) / 2, 2k); CSG nodes have none. */
+enum { F_PX, F_PY, F_PZ, F_R, F_EX, F_EY, F_EZ, F_K, F_RKH, F_K2 };
+
+static int node_slots(const lolb200_object* o) {
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: return 4;
+	case LOLB200_OBJ_BOX: return 7;
+	case LOLB200_OBJ_PLANE: return 1;
+	case LOLB200_OBJ_SMOOTH_UNION: return 3;
+	default: return 0;
+	}
+}
+
+static int field_slot(const lolb200_object* o, int f) {
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: return f == F_R ? 3 : f - F_PX;
+	case LOLB200_OBJ_BOX: return f == F_R ? 6 : f <= F_PZ ? 2 * (f - F_PX) : 2 * (f - F_EX) + 1;
+	case LOLB200_OBJ_PLANE: return 0;
+	default: return f - F_K;
+	}
+}
+
+static float field_value(const lolb200_object* o, int f) {
+	switch (f) {
+	case F_PX: case F_PY: case F_PZ: return o->point[f - F_PX];
+	case F_R: return o->radius;
+	case F_EX: case F_EY: case F_EZ: return o->point2[f - F_EX];
+	case F_K: return o->smoothness;
+	case F_RKH: return (1.0f / o->smoothness) * 0.5f; /* RN(1/k) / 2, see lol_smin_c */
+	default: return o->smoothness * 2.0f;
+	}
+}
+
+static const int lol_field_order[4][7] = {{F_PX, F_PY, F_PZ, F_R}, {F_PX, F_EX, F_PY, F_EY, F_PZ, F_EZ, F_R}, {F_PY}, {F_K, F_RKH, F_K2}};
+static const int* node_fields(const lolb200_object* o) {
+	return lol_field_order[o->type == LOLB200_OBJ_SPHERE ? 0 : o->type == LOLB200_OBJ_BOX ? 1 : o->type == LOLB200_OBJ_PLANE ? 2 : 3];
+}
+
+/* the constants of the paired subtrees (a, b): field by field, a's next to b's, at an
+ * even slot -- one 64-bit load hands the packed code its (low, high) operand */
+static void layout_pair(struct cgen* g, uint32_t a, uint32_t b) {
+	const lolb200_object *oa = &g->s->nodes[a], *ob = &g->s->nodes[b];
+	const int* fields = node_fields(oa);
+	if (oa->type != LOLB200_OBJ_SPHERE) {
+		layout_pair(g, (uint32_t)oa->a, (uint32_t)ob->a);
+		layout_pair(g, (uint32_t)oa->b, (uint32_t)ob->b);
+	}
+	if (node_slots(oa) && (g->nrow & 1u))
+		row_push(g, 0.f);
+	g->slot[a] = g->nrow;
+	g->slot[b] = g->nrow + 1;
+	g->stride[a] = g->stride[b] = 2;
+	for (int q = 0; q < node_slots(oa); q++) {
+		row_push(g, field_value(oa, fields[q]));
+		row_push(g, field_value(ob, fields[q]));
+	}
+}
+
+/* loop mode: the constants of the object rooted at idx go into the row, post-order */
+static void layout_node(struct cgen* g, uint32_t idx) {
+	const lolb200_object* o = &g->s->nodes[idx];
+	const int* fields = node_fields(o);
+	if (g->npairs && g->pair_of[idx]) {
+		const struct pair_plan* p = &g->pairs[(g->pair_of[idx] - 1) / 2];
+		if (idx == p->a) /* (b comes later in the tree; its slots exist by then) */
+			layout_pair(g, p->a, p->b);
+		return;
+	}
+	if (o->type != LOLB200_OBJ_SPHERE && o->type != LOLB200_OBJ_BOX && o->type != LOLB200_OBJ_PLANE) {
+		layout_node(g, (uint32_t)o->a);
+		layout_node(g, (uint32_t)o->b);
+	}
+	g->slot[idx] = g->nrow;
+	g->stride[idx] = 1;
+	for (int q = 0; q < node_slots(o); q++)
+		row_push(g, field_value(o, fields[q]));
+}
+
+/* field f of node idx as a float expression */
+static void ncst(struct cgen* g, uint32_t idx, int f) {
+	const lolb200_object* o = &g->s->nodes[idx];
+	if (!g->in_loop)
+		sb_float(g->out, field_value(o, f));
+	else
+		sb_printf(g->out, "LOL_TF(c[%zu])", g->slot[idx] + (size_t)g->stride[idx] * (size_t)field_slot(o, f));
 }
 
 static int is_pos_zero(float v) { return f2u(v) == 0u; }
 
 /* `x - c`; x - (+0) is x for every x, so it is dropped outside loops. */
-static void coord_minus(struct cgen* g, const char* x, float c) {
-	if (!g->in_loop && is_pos_zero(c)) {
+static void coord_minus(struct cgen* g, const char* x, uint32_t idx, int f) {
+	if (!g->in_loop && is_pos_zero(field_value(&g->s->nodes[idx], f))) {
 		sb_printf(g->out, "%s", x);
 		return;
 	}
 	sb_printf(g->out, "%s - ", x);
-	cst(g, c);
+	ncst(g, idx, f);
+}
+
+/* ---- pairs: two subtrees of one shape, one packed instruction stream ------------
+ * lol_render is bound by instruction issue (ncu: 94 % of the slots), and sm_100a's
+ * two-wide FP32 instructions do two IEEE operations per slot.  Variant 3 fills the
+ * halves with two RAYS and pays for it in registers and bookkeeping; here the halves
+ * are two SUBTREES of the same ray: spheres (0, 4) and (1, 5) of scene4's blob, the
+ * two halves of a balanced smooth-union tree.  Same operations, same order, same
+ * rounding per half -- only the instruction count changes (scene4's march loop:
+ * 174 -> 146).  Chosen by shape alone, so every row of a table loop pairs alike. */
+static int packable(const struct cgen* g, uint32_t idx, int div_ok) {
+	const lolb200_object* o = &g->s->nodes[idx];
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: return 1;
+	case LOLB200_OBJ_SMOOTH_UNION:
+		return div_ok && packable(g, (uint32_t)o->a, div_ok) && packable(g, (uint32_t)o->b, div_ok);
+	case LOLB200_OBJ_UNION:
+	case LOLB200_OBJ_INTERSECTION:
+	case LOLB200_OBJ_DIFFERENCE: return packable(g, (uint32_t)o->a, div_ok) && packable(g, (uint32_t)o->b, div_ok);
+	default: return 0;
+	}
+}
+
+static void signature(const lolb200_scene* s, uint32_t idx, struct sb* out);
+
+struct pair_cand {
+	uint32_t idx, size, order;
+	char* sig;
+};
+
+static uint32_t subtree_size(const lolb200_scene* s, uint32_t idx) {
+	const lolb200_object* o = &s->nodes[idx];
+	if (o->type == LOLB200_OBJ_SPHERE || o->type == LOLB200_OBJ_BOX || o->type == LOLB200_OBJ_PLANE)
+		return 1;
+	return 1 + subtree_size(s, (uint32_t)o->a) + subtree_size(s, (uint32_t)o->b);
+}
+
+static void collect_cands(const struct cgen* g, uint32_t idx, int div_ok, struct pair_cand* c, uint32_t* n) {
+	const lolb200_object* o = &g->s->nodes[idx];
+	if (packable(g, idx, div_ok)) {
+		struct sb sig = {0};
+		signature(g->s, idx, &sig);
+		c[*n].idx = idx;
+		c[*n].size = subtree_size(g->s, idx);
+		c[*n].order = *n;
+		c[*n].sig = sig.p;
+		++*n;
+	}
+	if (o->type != LOLB200_OBJ_SPHERE && o->type != LOLB200_OBJ_BOX && o->type != LOLB200_OBJ_PLANE) {
+		collect_cands(g, (uint32_t)o->a, div_ok, c, n);
+		collect_cands(g, (uint32_t)o->b, div_ok, c, n);
+	}
+}
+
+static int cand_cmp(const void* a, const void* b) {
+	const struct pair_cand *x = a, *y = b;
+	return x->size != y->size ? (x->size < y->size) - (x->size > y->size) : (x->order > y->order) - (x->order < y->order);
+}
+
+static void mark_subtree(const lolb200_scene* s, uint32_t idx, unsigned char* covered) {
+	const lolb200_object* o = &s->nodes[idx];
+	covered[idx] = 1;
+	if (o->type != LOLB200_OBJ_SPHERE && o->type != LOLB200_OBJ_BOX && o->type != LOLB200_OBJ_PLANE) {
+		mark_subtree(s, (uint32_t)o->a, covered);
+		mark_subtree(s, (uint32_t)o->b, covered);
+	}
+}
+
+/* Largest subtrees first: each packable subtree not yet inside a pair takes the next
+ * free subtree of the same shape (in tree order) as its partner. */
+static void plan_pairs(struct cgen* g, uint32_t root, int enabled) {
+	const uint32_t total = subtree_size(g->s, root);
+	struct pair_cand* c;
+	unsigned char* covered;
+	uint32_t n = 0;
+	g->npairs = 0;
+	if (!enabled || total < 2)
+		return;
+	c = malloc(sizeof *c * total);
+	collect_cands(g, root, enabled > 1 ? g->lay_div_ok : g->div_ok, c, &n);
+	if ((enabled > 1 ? g->lay_pack : g->pack) == 3) { /* pack_pairs = 3: leaves only (an A/B point) */
+		uint32_t m = 0;
+		for (uint32_t i = 0; i < n; i++)
+			if (c[i].size == 1)
+				c[m++] = c[i];
+			else
+				free(c[i].sig);
+		n = m;
+	}
+	if (n >= 2) {
+		covered = calloc(g->s->n_nodes, 1);
+		if (!g->pair_of)
+			g->pair_of = calloc(g->s->n_nodes, sizeof *g->pair_of);
+		g->pairs = realloc(g->pairs, sizeof *g->pairs * (n / 2));
+		qsort(c, n, sizeof *c, cand_cmp);
+		for (uint32_t i = 0; i < n; i++) {
+			if (covered[c[i].idx])
+				continue;
+			for (uint32_t j = i + 1; j < n && c[j].size == c[i].size; j++) {
+				if (covered[c[j].idx] || strcmp(c[i].sig, c[j].sig) != 0)
+					continue;
+				g->pairs[g->npairs].a = c[i].idx;
+				g->pairs[g->npairs].b = c[j].idx;
+				g->pairs[g->npairs].tmp = -1;
+				g->pair_of[c[i].idx] = 1 + 2 * (uint32_t)g->npairs;
+				g->pair_of[c[j].idx] = 2 + 2 * (uint32_t)g->npairs;
+				g->npairs++;
+				mark_subtree(g->s, c[i].idx, covered);
+				mark_subtree(g->s, c[j].idx, covered);
+				break;
+			}
+		}
+		free(covered);
+	}
+	for (uint32_t i = 0; i < n; i++)
+		free(c[i].sig);
+	free(c);
+}
+
+static void unplan_pairs(struct cgen* g) {
+	for (size_t i = 0; i < g->npairs; i++)
+		g->pair_of[g->pairs[i].a] = g->pair_of[g->pairs[i].b] = 0;
+	g->npairs = 0;
+}
+
+static void cgen_release(struct cgen* g) {
+	free(g->row);
+	free(g->slot);
+	free(g->stride);
+	free(g->pair_of);
+	free(g->pairs);
+	g->row = NULL;
+	g->slot = NULL;
+	g->stride = NULL;
+	g->pair_of = NULL;
+	g->pairs = NULL;
+	g->nrow = g->caprow = g->npairs = 0;
+}
+
+/* LOL_PC(i): the i-th constant pair of this function (lol_pairc[], emitted in front of it) */
+static size_t pair_const(struct cgen* g, float lo, float hi) {
+	struct pairc* pc = g->pc;
+	for (size_t i = 0; i < pc->n; i++)
+		if (pc->w[i][0] == f2u(lo) && pc->w[i][1] == f2u(hi))
+			return i;
+	if (pc->n == pc->cap) {
+		pc->cap = pc->cap ? pc->cap * 2 : 16;
+		pc->w = realloc(pc->w, pc->cap * sizeof *pc->w);
+	}
+	pc->w[pc->n][0] = f2u(lo);
+	pc->w[pc->n][1] = f2u(hi);
+	return pc->n++;
+}
+
+/* field f of nodes (a, b) as one lol_f2 expression */
+static void pcst(struct cgen* g, uint32_t a, uint32_t b, int f) {
+	if (g->in_loop) {
+		/* layout_pair put them side by side at an even slot */
+		sb_printf(g->out, "lol_ld2_(c + %zu)", g->slot[a] + 2u * (size_t)field_slot(&g->s->nodes[a], f));
+	} else {
+		const float va = field_value(&g->s->nodes[a], f), vb = field_value(&g->s->nodes[b], f);
+		sb_printf(g->out, "LOL_PC(%zu) /*%.9g, %.9g*/", pair_const(g, va, vb), (double)va, (double)vb);
+	}
+}
+
+/* `lhs - (field f of a, of b)`, both halves at once.  Outside loops: nothing when both
+ * are +0, a broadcast immediate when they are equal, else lhs + (-va, -vb) from the
+ * constant pairs (x - c and x + (-c) are the same IEEE operation). */
+static void pair_minus(struct cgen* g, const char* lhs, uint32_t a, uint32_t b, int f) {
+	const float va = field_value(&g->s->nodes[a], f), vb = field_value(&g->s->nodes[b], f);
+	if (g->in_loop) {
+		sb_printf(g->out, "%s - ", lhs);
+		pcst(g, a, b, f);
+	} else if (is_pos_zero(va) && is_pos_zero(vb)) {
+		sb_printf(g->out, "%s", lhs);
+	} else if (f2u(va) == f2u(vb)) {
+		sb_printf(g->out, "%s - ", lhs);
+		sb_float(g->out, va);
+	} else {
+		sb_printf(g->out, "%s + LOL_PC(%zu) /*-(%.9g, %.9g)*/", lhs, pair_const(g, -va, -vb), (double)va, (double)vb);
+	}
+}
+
+/* The subtrees rooted at a and b (one shape) evaluated together:
+ * `const lol_f2 pN = (dist(a, p), dist(b, p));`.  Returns N. */
+static int emit_pair(struct cgen* g, uint32_t a, uint32_t b) {
+	const lolb200_object *oa = &g->s->nodes[a], *ob = &g->s->nodes[b];
+	int me;
+	if (oa->type == LOLB200_OBJ_SPHERE) { /* sdSphere, sdf.h:8-10, twice */
+		char lhs[48];
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst lol_f2 qx%d = ", g->indent, me);
+		pair_minus(g, "lol_bc(x)", a, b, F_PX);
+		sb_printf(g->out, ", qy%d = ", me);
+		pair_minus(g, "lol_bc(y)", a, b, F_PY);
+		sb_printf(g->out, ", qz%d = ", me);
+		pair_minus(g, "lol_bc(z)", a, b, F_PZ);
+		sb_printf(g->out, ";\n%sconst lol_f2 s%d = lol_dot2(qx%d, qy%d, qz%d, qx%d, qy%d, qz%d);\n", g->indent, me, me,
+		          me, me, me, me, me);
+		sb_printf(g->out, "%slo = lol_min_halves(lo, s%d);\n", g->indent, me);
+		snprintf(lhs, sizeof lhs, "lol_sqrt_fast2(s%d)", me);
+		sb_printf(g->out, "%sconst lol_f2 p%d = ", g->indent, me);
+		pair_minus(g, lhs, a, b, F_R);
+		sb_printf(g->out, ";\n");
+		return me;
+	}
+	{
+		const int pa = emit_pair(g, (uint32_t)oa->a, (uint32_t)ob->a);
+		const int pb = emit_pair(g, (uint32_t)oa->b, (uint32_t)ob->b);
+		me = g->tmp++;
+		if (oa->type != LOLB200_OBJ_SMOOTH_UNION) {
+			sb_printf(g->out, "%sconst lol_f2 p%d = lol_csg_%s(p%d, p%d);\n", g->indent, me,
+			          oa->type == LOLB200_OBJ_UNION ? "union" : oa->type == LOLB200_OBJ_INTERSECTION ? "inter" : "diff",
+			          pa, pb);
+		} else if (!g->in_loop && f2u(oa->smoothness) == f2u(ob->smoothness)) {
+			sb_printf(g->out, "%sconst lol_f2 p%d = lol_smin_c2(p%d, p%d, ", g->indent, me, pa, pb);
+			ncst(g, a, F_K);
+			sb_printf(g->out, ", ");
+			ncst(g, a, F_RKH);
+			sb_printf(g->out, ", ");
+			ncst(g, a, F_K2);
+			sb_printf(g->out, ");\n");
+		} else {
+			sb_printf(g->out, "%sconst lol_f2 p%d = lol_smin_c2v(p%d, p%d, ", g->indent, me, pa, pb);
+			pcst(g, a, b, F_K);
+			sb_printf(g->out, ", ");
+			pcst(g, a, b, F_RKH);
+			sb_printf(g->out, ", ");
+			pcst(g, a, b, F_K2);
+			sb_printf(g->out, ");\n");
+		}
+	}
+	return me;
 }
 
 /* get_obj_dist (naive_renderer.c:10-28), one object -> `const float tN = ...;`.
@@ -159,17 +488,27 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 	const char* T = g->two ? "lol_f2" : "float";
 	int me;
 
+	if (g->npairs && g->pair_of[idx]) {
+		/* one half of a planned pair: both subtrees are evaluated where the first is needed */
+		struct pair_plan* p = &g->pairs[(g->pair_of[idx] - 1) / 2];
+		if (p->tmp < 0)
+			p->tmp = emit_pair(g, p->a, p->b);
+		me = g->tmp++;
+		sb_printf(g->out, "%sconst float t%d = lol_%s(p%d);\n", g->indent, me,
+		          ((g->pair_of[idx] - 1) & 1) ? "hi" : "lo", p->tmp);
+		return me;
+	}
 	switch (o->type) {
 	case LOLB200_OBJ_SPHERE: /* sdSphere, sdf.h:8-10 */
 		me = g->tmp++;
 		if (g->fast) {
 			/* same operations; the squared length also feeds the range guard */
 			sb_printf(g->out, "%sconst %s qx%d = ", g->indent, T, me);
-			coord_minus(g, "x", o->point[0]);
+			coord_minus(g, "x", idx, F_PX);
 			sb_printf(g->out, ", qy%d = ", me);
-			coord_minus(g, "y", o->point[1]);
+			coord_minus(g, "y", idx, F_PY);
 			sb_printf(g->out, ", qz%d = ", me);
-			coord_minus(g, "z", o->point[2]);
+			coord_minus(g, "z", idx, F_PZ);
 			sb_printf(g->out, ";\n%sconst %s s%d = lol_dot%s(qx%d, qy%d, qz%d, qx%d, qy%d, qz%d);\n",
 			          g->indent, T, me, g->two ? "2" : "", me, me, me, me, me, me);
 			if (g->two)
@@ -178,57 +517,55 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 				sb_printf(g->out, "%slo = fminf(lo, s%d);\n", g->indent, me);
 			sb_printf(g->out, "%sconst %s t%d = lol_sqrt_fast%s(s%d) - ", g->indent, T, me,
 			          g->two ? "2" : "", me);
-			cst(g, o->radius);
+			ncst(g, idx, F_R);
 			sb_printf(g->out, ";\n");
 			return me;
 		}
 		sb_printf(g->out, "%sconst float t%d = lol_len(", g->indent, me);
-		coord_minus(g, "x", o->point[0]);
+		coord_minus(g, "x", idx, F_PX);
 		sb_printf(g->out, ", ");
-		coord_minus(g, "y", o->point[1]);
+		coord_minus(g, "y", idx, F_PY);
 		sb_printf(g->out, ", ");
-		coord_minus(g, "z", o->point[2]);
+		coord_minus(g, "z", idx, F_PZ);
 		sb_printf(g->out, ") - ");
-		cst(g, o->radius);
+		ncst(g, idx, F_R);
 		sb_printf(g->out, ";\n");
 		return me;
 	case LOLB200_OBJ_BOX: /* sdRoundBox, sdf.h:18-22 */
 		me = g->tmp++;
 		if (g->two) {
-			/* no two-wide abs/max: the box runs per half on the packed coordinates.  The
-			 * constants are read in the scalar form's order (centre, extent per axis, then
-			 * the radius): in a table loop both forms read the same row. */
+			/* no two-wide abs/max: the box runs per half on the packed coordinates */
 			sb_printf(g->out, "%sconst lol_f2 t%d = lol_roundbox2(", g->indent, me);
 			for (int k = 0; k < 3; k++) {
-				coord_minus(g, k == 0 ? "x" : k == 1 ? "y" : "z", o->point[k]);
+				coord_minus(g, k == 0 ? "x" : k == 1 ? "y" : "z", idx, F_PX + k);
 				sb_printf(g->out, ", ");
-				cst(g, o->point2[k]);
+				ncst(g, idx, F_EX + k);
 				sb_printf(g->out, ", ");
 			}
-			cst(g, o->radius);
+			ncst(g, idx, F_R);
 			sb_printf(g->out, ");\n");
 			return me;
 		}
 		sb_printf(g->out, "%sconst float t%d = lol_roundbox(fabsf(", g->indent, me);
-		coord_minus(g, "x", o->point[0]);
+		coord_minus(g, "x", idx, F_PX);
 		sb_printf(g->out, ") - ");
-		cst(g, o->point2[0]);
+		ncst(g, idx, F_EX);
 		sb_printf(g->out, ", fabsf(");
-		coord_minus(g, "y", o->point[1]);
+		coord_minus(g, "y", idx, F_PY);
 		sb_printf(g->out, ") - ");
-		cst(g, o->point2[1]);
+		ncst(g, idx, F_EY);
 		sb_printf(g->out, ", fabsf(");
-		coord_minus(g, "z", o->point[2]);
+		coord_minus(g, "z", idx, F_PZ);
 		sb_printf(g->out, ") - ");
-		cst(g, o->point2[2]);
+		ncst(g, idx, F_EZ);
 		sb_printf(g->out, ", ");
-		cst(g, o->radius);
+		ncst(g, idx, F_R);
 		sb_printf(g->out, ");\n");
 		return me;
 	case LOLB200_OBJ_PLANE: /* point.y, naive_renderer.c:19-20 */
 		me = g->tmp++;
 		sb_printf(g->out, "%sconst %s t%d = ", g->indent, T, me);
-		coord_minus(g, "y", o->point[1]);
+		coord_minus(g, "y", idx, F_PY);
 		sb_printf(g->out, ";\n");
 		return me;
 	case LOLB200_OBJ_UNION:
@@ -245,25 +582,47 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 	default: { /* sminf(a, b, k), naive_renderer.c:21-24 */
 		int a = emit_node(g, (uint32_t)o->a);
 		int b = emit_node(g, (uint32_t)o->b);
-		const float rk = 1.0f / o->smoothness;
 		me = g->tmp++;
 		if (g->fast && g->div_ok) {
 			sb_printf(g->out, "%sconst %s t%d = lol_smin_c%s(t%d, t%d, ", g->indent, T, me,
 			          g->two ? "2" : "", a, b);
-			cst(g, o->smoothness);
+			ncst(g, idx, F_K);
 			sb_printf(g->out, ", ");
-			cst(g, rk);
+			ncst(g, idx, F_RKH);
+			sb_printf(g->out, ", ");
+			ncst(g, idx, F_K2);
 			sb_printf(g->out, ");\n");
 		} else {
 			sb_printf(g->out, "%sconst %s t%d = lol_smin%s(t%d, t%d, ", g->indent, T, me,
 			          g->two ? "2" : "", a, b);
-			cst(g, o->smoothness);
-			cst_skip(g, rk);
+			ncst(g, idx, F_K);
 			sb_printf(g->out, ");\n");
 		}
 		return me;
 	}
 	}
+}
+
+/* One top-level object: its row layout (loop mode), its pairs, its code. */
+static int emit_object(struct cgen* g, uint32_t root) {
+	const int pairing = g->pack && g->fast && !g->two;
+	int t;
+	if (g->in_loop) {
+		if (!g->slot) {
+			g->slot = calloc(g->s->n_nodes ? g->s->n_nodes : 1, sizeof *g->slot);
+			g->stride = calloc(g->s->n_nodes ? g->s->n_nodes : 1, 1);
+		}
+		/* the layout follows the guarded form's pairs whichever form is being written */
+		plan_pairs(g, root, g->lay_pack ? 2 : 0);
+		layout_node(g, root);
+		while (g->nrow % 4) /* rows of 16-byte multiples: the loads of neighbouring slots merge */
+			row_push(g, 0.f);
+		unplan_pairs(g);
+	}
+	plan_pairs(g, root, pairing);
+	t = emit_node(g, root);
+	unplan_pairs(g);
+	return t;
 }
 
 /* Shape of a subtree without its constants: objects with equal signatures run
@@ -374,7 +733,8 @@ static void bound_row(const lolb200_scene* s, uint32_t idx, float row[LOL_BOUND_
 		row[k] = (float)((lo[k] + hi[k]) * 0.5);
 		row[3 + k] = (float)((hi[k] - lo[k]) * 0.5 * 1.002 + 0.002 * (l1 + 1.0) + 1e-6);
 	}
-	row[6] = (float)(M * 1.002 + 1e-6);
+	/* slot 6 is the margin times the kernel's 1.004 (lol_box_skips: u = best * 1.004 + m1) */
+	row[6] = nextafterf((float)(M * 1.002 + 1e-6) * 1.004f, INFINITY);
 }
 
 /* ---- two-level pruning: rows sorted along a Morton curve, groups of neighbours ---- */
@@ -501,7 +861,7 @@ static float est_node(const lolb200_scene* s, uint32_t idx, const float p[3]) {
 static int est_box_skips(const float p[3], const float b[7], float best) {
 	const float q[3] = {fmaxf(fabsf(p[0] - b[0]) - b[3], 0.f), fmaxf(fabsf(p[1] - b[1]) - b[4], 0.f),
 	                    fmaxf(fabsf(p[2] - b[2]) - b[5], 0.f)};
-	const float u = (best + b[6]) * 1.004f;
+	const float u = best * 1.004f + b[6];
 	return u > 0.f && q[0] * q[0] + q[1] * q[1] + q[2] * q[2] > u * u;
 }
 
@@ -617,7 +977,7 @@ static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, co
 		sb_printf(body, ") {\n");
 		snprintf(ind, sizeof ind, "%s\t\t", tabs);
 	}
-	int t = emit_node(g, g->s->objects[k]);
+	int t = emit_object(g, g->s->objects[k]);
 	if (two) {
 		char tA[64] = "", tB[64] = "";
 		if (tie_aware) {
@@ -691,10 +1051,17 @@ static void tab_u32(struct tabs* T, uint32_t v) {
 static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_scene* s,
                         int loop_threshold, const char* name, const char* attrs, int fast,
                         int div_ok, const char* fallback, int prune, int two, int smem_ok,
-                        struct est_memo* memo) {
+                        struct est_memo* memo, int pack, int lay_pack, int lay_div_ok) {
 	struct sb body = {0};
 	struct tabs tables = {{0}, {0}, 0};
-	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok, .two = two};
+	struct pairc pc = {0};
+	/* pack_pairs = 1 packs where it was measured to pay: inside table loops (B200, 4K: 1024
+	 * spheres 48.6 -> 45.9 ms, CSG 45.8 -> 43.5 ms).  Straight-line scenes lose a few
+	 * percent (scene4 2.26 -> 2.36 ms with 16 % fewer instructions: the packed instructions
+	 * keep the FMA pipe as busy as the scalar ones did and their dependent chains issue
+	 * at 0.3-0.45 per clock, profiles/r01_ubench_f32x2.txt), so they pack only on request. */
+	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok, .two = two, .pack = pack >= 2 ? pack : 0, .pc = &pc,
+		                 .lay_pack = lay_pack, .lay_div_ok = lay_div_ok};
 	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
 	int run_no = 0;
 
@@ -880,13 +1247,14 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				for (uint32_t k = i; k < j; k++) {
 					struct sb scratch = {0};
 					struct cgen r = {.s = s, .out = (k == i) ? &body : &scratch, .in_loop = 1,
-					                 .indent = "\t\t", .fast = fast, .div_ok = div_ok, .two = two};
+					                 .indent = "\t\t", .fast = fast, .div_ok = div_ok, .two = two, .pack = pack, .pc = &pc,
+		                 .lay_pack = lay_pack, .lay_div_ok = lay_div_ok};
 					if (k == i)
 						sb_printf(&body,
 						          "\t{\n#pragma unroll 1\n\tfor (int i = 0; i < %u; ++i) {\n"
 						          "\t\tconst lol_u32* c = lol_run%d + i * LOL_RUN%d_STRIDE;\n",
 						          n, run_no, run_no);
-					int t = emit_node(&r, s->objects[k]);
+					int t = emit_object(&r, s->objects[k]);
 					if (k == i && two)
 						sb_printf(&body,
 						          "\t\tconst float a_ = lol_lo(t%d), b_ = lol_hi(t%d);\n"
@@ -903,7 +1271,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					sb_printf(&tables.words, "\n\t");
 					for (size_t q = 0; q < r.nrow; q++)
 						tab_float(&tables, r.row[q]);
-					free(r.row);
+					cgen_release(&r);
 					free(scratch.p);
 				}
 				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
@@ -947,7 +1315,8 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					const uint32_t k = i + order[q];
 					struct sb scratch = {0};
 					struct cgen r = {.s = s, .out = (q == 0) ? &body : &scratch, .in_loop = 1,
-					                 .indent = "\t\t\t", .fast = fast, .div_ok = div_ok, .two = two};
+					                 .indent = "\t\t\t", .fast = fast, .div_ok = div_ok, .two = two, .pack = pack, .pc = &pc,
+		                 .lay_pack = lay_pack, .lay_div_ok = lay_div_ok};
 					const char* best_args = two ? "bestA, bestB" : "best";
 					const char* sfx = two ? "2" : "";
 					if (q == 0) {
@@ -1012,7 +1381,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					cst_raw(&r, k + 1);
 					if (q == 0)
 						sb_printf(&body, ";\n");
-					int t = emit_node(&r, s->objects[k]);
+					int t = emit_object(&r, s->objects[k]);
 					if (q == 0 && two)
 						sb_printf(&body,
 						          "\t\t\tconst float a_ = lol_lo(t%d), b_ = lol_hi(t%d);\n"
@@ -1030,7 +1399,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					sb_printf(&tables.words, "\n\t");
 					for (size_t w = 0; w < r.nrow; w++)
 						tab_float(&tables, r.row[w]);
-					free(r.row);
+					cgen_release(&r);
 					free(scratch.p);
 				}
 				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
@@ -1094,6 +1463,15 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			sb_putn(tables_out, tables.defs.p, tables.defs.len);
 		}
 	}
+	if (pc.n) {
+		/* the constant pairs of the packed code: ptxas keeps them in uniform register pairs */
+		sb_printf(out, "__constant__ __align__(8) lol_u32 lol_pairc[] = {");
+		for (size_t i = 0; i < pc.n; i++)
+			sb_printf(out, "%s0x%08xu, 0x%08xu,", i % 4 ? " " : "\n\t", pc.w[i][0], pc.w[i][1]);
+		sb_printf(out, "\n};\n");
+	}
+	free(pc.w);
+	cgen_release(&g);
 	sb_putn(out, body.p, body.len);
 
 	for (uint32_t i = 0; i < s->n_objects; i++)
@@ -1199,7 +1577,7 @@ static int guard_pays(const lolb200_scene* s) {
 }
 
 static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
-                     int prune, int two, int smem_ok) {
+                     int prune, int two, int smem_ok, int pack) {
 	struct sb tables = {0};
 	struct est_memo memo = {{0, 0}, {0, 0}, {NULL, NULL}};
 	if (guarded == 1 && !guard_pays(s) && !two)
@@ -1208,19 +1586,19 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		struct sb ref = {0};
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
-		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok, &memo);
+		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, pack, div_ok);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
 		emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf", "__forceinline__", 1, div_ok,
-		            "lol_sdf_ref", prune, 0, smem_ok, &memo);
+		            "lol_sdf_ref", prune, 0, smem_ok, &memo, pack, pack, div_ok);
 		if (two)
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf2", "__forceinline__", 1, div_ok,
-			            "lol_sdf_ref", prune, 1, smem_ok, &memo);
+			            "lol_sdf_ref", prune, 1, smem_ok, &memo, 0, pack, div_ok);
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
 		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
-		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo);
+		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, 0, 0);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
@@ -1436,7 +1814,8 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
-	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */);
+	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */,
+	         o.pack_pairs);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

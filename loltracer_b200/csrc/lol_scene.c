@@ -98,6 +98,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->guarded_fastpath = 1;
 	o->prune_bounds = 1;
 	o->roll_phases = 1;
+	o->pack_pairs = 1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

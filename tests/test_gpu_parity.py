@@ -341,6 +341,34 @@ def test_two_ray_kernel_4k_bit_identical_to_variant1(name, scenes_dir):
     assert {k: v for k, v in ca.items() if k != "skipped_flops"} == {k: v for k, v in cb.items() if k != "skipped_flops"}
 
 
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic", "synthetic_csg"])
+def test_packed_pairs_bit_identical_to_scalar_code(name, scenes_dir):
+    """pack_pairs: two same-shaped subtrees of an object in the halves of FADD2/FMUL2/FFMA2
+    (scene4: spheres (0,4), (1,5) and their two smooth unions; the synthetic scenes: the two
+    halves of every balanced tree, constants read as 64-bit pairs from the row) against the
+    scalar code, guard forced on so that every example takes the packed forms where it can:
+    the SAME frame, distances, ids and step counts at 3840x2160, and the oracle's."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    w, h = (3840, 2160) if not name.startswith("synthetic") else (960, 540)
+    scene = (lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name.endswith("csg"))) if name.startswith("synthetic")
+             else lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol")))
+    a = _render(lb, scene, w, h, options=lb.Options.default(variant=1, guarded_fastpath=2, pack_pairs=0))
+    b = _render(lb, scene, w, h, options=lb.Options.default(variant=1, guarded_fastpath=2, pack_pairs=2))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=2, pack_pairs=2))
+    if name not in ("scene", "scene2"):  # their spheres are separate top-level objects: nothing to pair
+        head = src.split("//@@SCENE@@")[0]
+        assert "lol_sqrt_fast2(" in head[head.index("__forceinline__ float lol_sdf("):]
+    for key in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+    if not name.startswith("synthetic"):
+        _check(b, ol.port_render(scene, w, h))
+    a["renderer"].close()
+    b["renderer"].close()
+
+
 def test_host_surface_follows_a_resizing_window(scenes_dir):
     """main.c re-fetches the surface every frame and the window is resizable
     (main.c:182): the host-surface entry point must follow changes of size, pitch and

@@ -262,3 +262,62 @@ def test_points_outside_the_guard_take_the_ieee_path(name, variant, scenes_dir, 
     same = (d.view(np.uint32) == wd.view(np.uint32)) | (np.isnan(d) & np.isnan(wd))
     assert same.all(), (pts[~same], d[~same], wd[~same])
     assert np.array_equal(ids, wi)
+
+
+def test_packed_pairs_structure(scenes_dir):
+    """pack_pairs pairs subtrees by SHAPE: scene4's blob U(U(S,S),U(S,U(S,S))) evaluates
+    U(S0,S1) with U(S4,S5) -- two packed sphere pairs and one packed smooth union -- and
+    keeps S3 and the two outer unions scalar; scene3's U(S,S) becomes one sphere pair; the
+    1024-sphere scene's balanced trees pack completely (4 + 2 + 1 packed nodes, one scalar
+    root) and read their constants as 64-bit pairs from rows of 16-byte multiples -- by
+    default, because that is where packing was measured to pay; straight-line scenes pack
+    on request (pack_pairs=2).  Off, no packed instruction is emitted."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    def fast_fn(src):
+        body = src.split("//@@SCENE@@")[0]
+        return body[body.index("__forceinline__ float lol_sdf("):]
+
+    s4 = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
+    f = fast_fn(lb.lower_cuda(s4, lb.Options.default(pack_pairs=2)))
+    assert f.count("lol_sqrt_fast2(") == 2 and f.count("lol_smin_c2(") == 1
+    assert f.count("lol_sqrt_fast(") == 1 and f.count("lol_smin_c(") == 2
+    assert "lol_u32 lol_pairc[] = {" in lb.lower_cuda(s4, lb.Options.default(pack_pairs=2))
+    # the default packs inside table loops only (measured: straight-line scenes lose a few percent)
+    assert "lol_sqrt_fast2(" not in fast_fn(lb.lower_cuda(s4, lb.Options.default()))
+    f = fast_fn(lb.lower_cuda(s4, lb.Options.default(pack_pairs=3)))  # leaves only
+    assert f.count("lol_sqrt_fast2(") == 2 and f.count("lol_smin_c2(") == 0 and f.count("lol_smin_c(") == 4
+    off = lb.lower_cuda(s4, lb.Options.default(pack_pairs=0)).split("//@@SCENE@@")[0]
+    assert "lol_u32 lol_pairc[] = {" not in off
+    off = fast_fn(lb.lower_cuda(s4, lb.Options.default(pack_pairs=0)))
+    assert "lol_sqrt_fast2(" not in off and off.count("lol_sqrt_fast(") == 5
+
+    s3 = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    f = fast_fn(lb.lower_cuda(s3, lb.Options.default(pack_pairs=2)))
+    assert f.count("lol_sqrt_fast2(") == 1 and f.count("lol_smin_c(") == 1
+
+    syn = lb.Scene.from_string(scenegen.synthetic_scene_text())
+    src = lb.lower_cuda(syn, lb.Options.default(variant=1))
+    f = fast_fn(src)
+    assert f.count("lol_sqrt_fast2(") == 4 and f.count("lol_smin_c2v(") == 3 and f.count("lol_smin_c(") == 1
+    assert "lol_ld2_(c + 8)" in f
+    stride = int(re.search(r"#define LOL_RUN0_STRIDE (\d+)", src).group(1))
+    assert stride % 4 == 0
+    # the IEEE fallback reads the same rows: a.x at slot 8, b.x next to it, a.y two further on
+    ref = src.split("//@@SCENE@@")[0]
+    ref = ref[ref.index("lol_u64 lol_sdf_ref("):ref.index("__forceinline__ float lol_sdf(")]
+    assert "LOL_TF(c[8])" in ref and "LOL_TF(c[9])" in ref and "LOL_TF(c[10])" in ref
+
+
+def test_folded_smin_equals_reference(tmp_path):
+    """lol_smin_c's two folded operations (.5f * (b - a) / k as one proved division by 2k,
+    b - n * h for b + (a - b) * h) against sminf as float.h:29-33 computes it: bit-identical
+    on 30 M operand pairs per run (random bits, nearly equal, equal, +-0, tiny), for ten
+    smoothness values.  The helper's main() returns non-zero on the first mismatch."""
+    exe = tmp_path / "smin_fold_check"
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", str(exe),
+                           os.path.join(ROOT, "tests", "helpers", "smin_fold_check.c"), "-lm"])
+    out = subprocess.run([str(exe), "3000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " 0 mismatches" in out.stdout

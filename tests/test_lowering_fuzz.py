@@ -2,7 +2,8 @@
 (host shim, tests/oracle_lib.py) must equal the oracle's sdf() bit for bit on every point --
 for straight-line code and forced table loops, with every pruning device on (boxes around
 objects and groups, Morton-sorted rows, last-winner hints, tie-aware updates), for one ray
-and for two rays per call, with the reference's node types and the CSG extensions.
+and for two rays per call, with same-shaped subtrees evaluated as packed pairs and one by
+one, with the reference's node types and the CSG extensions.
 
 Seeded numpy, not hypothesis: each case costs a g++ run, so the set is fixed and small.
 """
@@ -122,11 +123,13 @@ def test_random_scenes_lower_exactly(seed, extensions, tmp_path):
     pts = np.concatenate([rng.uniform(-30, 30, (600, 3)), rng.normal(0, 2.5, (1200, 3)) + [0, 1, -5],
                           rng.uniform(-8, 8, (400, 3)) * [1, 0.01, 1] + [0, -1, -5]]).astype(np.float32)
     want_d, want_id = oracle_sdf(scene, pts)
-    # (variant, loop threshold, pruning): loops forced from 2 same-shaped neighbours on
-    for variant, loops, prune in [(1, 0, 2), (1, 2, 2), (3, 2, 2), (1, 2, 0), (3, 0, 1)]:
-        opt = lb.Options.default(variant=variant, loop_threshold=loops, prune_bounds=prune, guarded_fastpath=2)
+    # (variant, loop threshold, pruning, packed pairs): loops forced from 2 same-shaped neighbours on
+    for variant, loops, prune, pack in [(1, 0, 2, 2), (1, 2, 2, 2), (3, 2, 2, 1), (1, 2, 0, 1), (3, 0, 1, 1),
+                                        (1, 0, 2, 0), (1, 2, 2, 0), (1, 2, 1, 3)]:
+        opt = lb.Options.default(variant=variant, loop_threshold=loops, prune_bounds=prune, guarded_fastpath=2,
+                                 pack_pairs=pack)
         src = lb.lower_cuda(scene, opt)
-        L = ol.cpu_sdf(tmp_path, src, f"fz{seed}{int(extensions)}_{variant}{loops}{prune}")
+        L = ol.cpu_sdf(tmp_path, src, f"fz{seed}{int(extensions)}_{variant}{loops}{prune}{pack}")
         d = np.zeros(len(pts), np.float32)
         ids = np.zeros(len(pts), np.uint32)
         fn = L.eval2 if "lol_sdf2(" in src.split("//@@SCENE@@")[0] and variant == 3 else L.eval
@@ -149,8 +152,9 @@ def test_random_scenes_render_like_the_oracle(seed, extensions):
     scene = lb.Scene.from_string(random_scene(seed + (100 if extensions else 0), extensions, fixed_head=False))
     w, h = 200, 112
     want = ol.port_render(scene, w, h)
-    for variant, loops, prune in [(1, 2, 2), (3, 2, 2), (1, 0, 1)]:
+    for variant, loops, prune, pack in [(1, 2, 2, 2), (3, 2, 2, 1), (1, 0, 1, 2), (1, 2, 2, 0), (1, 0, 2, 0)]:
         got = _render(lb, scene, w, h, options=lb.Options.default(variant=variant, loop_threshold=loops,
-                                                                  prune_bounds=prune, guarded_fastpath=2))
+                                                                  prune_bounds=prune, guarded_fastpath=2,
+                                                                  pack_pairs=pack))
         _check(got, want)
         got["renderer"].close()
