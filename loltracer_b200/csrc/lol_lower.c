@@ -1774,6 +1774,10 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_printf(&out, "#define LOL_SHADOW_EARLY %d\n", o.shadow_early_out != 0);
 	sb_printf(&out, "#define LOL_COUNTERS %d\n", o.counters != 0);
 	sb_printf(&out, "#define LOL_VARIANT %d\n", variant);
+	sb_printf(&out, "#define LOL_DIV_PRETEST %d\n", variant == 1 && o.arith == LOLB200_ARITH_EXACT && o.shadow_early_out != 0 &&
+	                                                  o.shadow_div_pretest != 0);
+	sb_printf(&out, "#define LOL_SHARE_FIRST %d\n#define LOL_SDF_FLOPS %lluu\n", variant == 1 && o.share_first_step != 0,
+	          (unsigned long long)lolb200_scene_flops_per_eval(s));
 	{
 		/* CTA shape.  Variant 3 holds two rays per thread (about twice the
 		 * registers): 128-thread CTAs let the register file be divided more finely. */

@@ -99,6 +99,8 @@ void lolb200_options_default(lolb200_options* o) {
 	o->prune_bounds = 1;
 	o->roll_phases = 1;
 	o->pack_pairs = 1;
+	o->share_first_step = 1;
+	o->shadow_div_pretest = 1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

@@ -369,6 +369,34 @@ def test_packed_pairs_bit_identical_to_scalar_code(name, scenes_dir):
     b["renderer"].close()
 
 
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
+def test_shared_first_step_and_division_pretest_do_not_change_the_frame(name, scenes_dir):
+    """share_first_step: step 1 of every primary ray is sdf(camera position); one thread per
+    CTA evaluates it and every ray takes it from shared memory.  shadow_div_pretest: the shadow
+    march divides (50 * d) / t only when a multiplication cannot prove that the quotient leaves
+    res alone.  Against every ray evaluating and dividing everything itself: the same frame,
+    distances, ids and step counts (the shared step still counts as a step), also from a
+    camera inside an object, where the march ends on step 1."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    w, h = (1920, 1080) if name != "synthetic" else (480, 270)
+    scene = (lb.Scene.from_string(scenegen.synthetic_scene_text()) if name == "synthetic" else
+             lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol")))
+    cams = [None, lb.Camera.make([0, 1, -6], [0.2, -0.1, -1], scene.struct.camera.fov)]
+    for cam in cams:
+        a = _render(lb, scene, w, h, camera=cam,
+                    options=lb.Options.default(variant=1, share_first_step=0, shadow_div_pretest=0))
+        b = _render(lb, scene, w, h, camera=cam, options=lb.Options.default(variant=1))
+        src = lb.lower_cuda(scene, lb.Options.default(variant=1))
+        assert "#define LOL_SHARE_FIRST 1" in src and "#define LOL_DIV_PRETEST 1" in src
+        for key in ("rgba", "id", "nprimary", "nshadow"):
+            assert np.array_equal(a[key], b[key]), key
+        assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+        a["renderer"].close()
+        b["renderer"].close()
+
+
 def test_host_surface_follows_a_resizing_window(scenes_dir):
     """main.c re-fetches the surface every frame and the window is resizable
     (main.c:182): the host-surface entry point must follow changes of size, pitch and
@@ -438,6 +466,8 @@ def test_straight_line_box_tests_do_not_change_the_frame(name, scenes_dir):
     ("scene4", (3e19, 1, 0), (-1, 0, 0)),        # beyond 2^60: the guard's coordinate range
     ("scene2", (0, 5, -6), (0, -1, 0)),          # straight down: cross(dir, up) = 0, a NaN camera basis
     ("scene", (2, 2, -10), (0, 0, -1)),          # inside the round box
+    ("scene", (-0.0, 0, -0.0), (0, 0, -1)),      # -0 + rd * 0 is +0 or -0 depending on rd: the shared first
+    ("scene4", (-0.0, 6, 3), (0.3, -0.7, -1)),   # step (share_first_step) must stand aside
 ])
 @pytest.mark.parametrize("variant", [1, 3])
 def test_cameras_outside_the_fast_forms_ranges(name, point, direction, variant, scenes_dir):

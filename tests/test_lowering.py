@@ -321,3 +321,16 @@ def test_folded_smin_equals_reference(tmp_path):
     out = subprocess.run([str(exe), "3000000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert " 0 mismatches" in out.stdout
+
+
+def test_shadow_division_pretest_never_skips_a_needed_division(tmp_path):
+    """LOL_DIV_PRETEST (lol_kernel.cuh, shadow march): whenever the multiplication test says
+    "the quotient cannot lower res", minf(res, num / t) as float.h:6-13 computes it returns res
+    bit for bit -- 20 M cases: random bits, plausible magnitudes, and quotients within +-2^-19
+    of res where the 2^-21 margin decides."""
+    exe = tmp_path / "div_pretest_check"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe),
+                           os.path.join(ROOT, "tests", "helpers", "div_pretest_check.c"), "-lm"])
+    out = subprocess.run([str(exe), "20000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " 0 mismatches" in out.stdout
