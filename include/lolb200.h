@@ -204,14 +204,18 @@ typedef struct lolb200_options {
 	                            instruction, so results are bit-identical).
 	                            1 = where it pays (inside table loops), 2 =
 	                            everywhere, 3 = everywhere, leaves only, 0 = never */
-	int32_t share_first_step;/* 1: step 1 of every primary ray evaluates sdf() at the
+	int32_t share_first_step;/* step 1 of every primary ray evaluates sdf() at the
 	                            camera position (ro + rd * 0): it is evaluated once
 	                            per CTA and shared (variant 1; exact, see
-	                            lol_kernel.cuh); 0: every ray evaluates it        */
+	                            lol_kernel.cuh).  1 = where it pays (scenes without
+	                            table loops), 2 = always, 0 = never               */
 	int32_t shadow_div_pretest; /* 1: the shadow march divides (50 * d) / t only when
 	                            the quotient can lower res; a multiplication with a
 	                            2^-21 margin proves the other steps (exact; variant
-	                            1, exact arithmetic, with shadow_early_out)        */
+	                            1, exact arithmetic, with shadow_early_out).
+	                            Measured slower on B200 (scene4 4K 2.149 -> 2.171
+	                            ms: the divergent branch costs more than the six
+	                            divisions in seven it saves), so off by default    */
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

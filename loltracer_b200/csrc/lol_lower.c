@@ -1776,7 +1776,10 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_printf(&out, "#define LOL_VARIANT %d\n", variant);
 	sb_printf(&out, "#define LOL_DIV_PRETEST %d\n", variant == 1 && o.arith == LOLB200_ARITH_EXACT && o.shadow_early_out != 0 &&
 	                                                  o.shadow_div_pretest != 0);
-	sb_printf(&out, "#define LOL_SHARE_FIRST %d\n#define LOL_SDF_FLOPS %lluu\n", variant == 1 && o.share_first_step != 0,
+	/* share_first_step = 1: where it was measured to pay (B200, 4K: scene 0.694 -> 0.679 ms, scene4
+	 * 2.149 -> 2.129 ms; scene2 loses 0.8 %, the table-loop scenes more); 2 forces it */
+	sb_printf(&out, "#define LOL_SHARE_FIRST %d\n#define LOL_SDF_FLOPS %lluu\n",
+	          variant == 1 && (o.share_first_step >= 2 || (o.share_first_step == 1 && !has_table_loop(s, threshold))),
 	          (unsigned long long)lolb200_scene_flops_per_eval(s));
 	{
 		/* CTA shape.  Variant 3 holds two rays per thread (about twice the

@@ -100,7 +100,6 @@ void lolb200_options_default(lolb200_options* o) {
 	o->roll_phases = 1;
 	o->pack_pairs = 1;
 	o->share_first_step = 1;
-	o->shadow_div_pretest = 1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

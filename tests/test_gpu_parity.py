@@ -387,8 +387,9 @@ def test_shared_first_step_and_division_pretest_do_not_change_the_frame(name, sc
     for cam in cams:
         a = _render(lb, scene, w, h, camera=cam,
                     options=lb.Options.default(variant=1, share_first_step=0, shadow_div_pretest=0))
-        b = _render(lb, scene, w, h, camera=cam, options=lb.Options.default(variant=1))
-        src = lb.lower_cuda(scene, lb.Options.default(variant=1))
+        on = lb.Options.default(variant=1, share_first_step=2, shadow_div_pretest=1)
+        b = _render(lb, scene, w, h, camera=cam, options=on)
+        src = lb.lower_cuda(scene, on)
         assert "#define LOL_SHARE_FIRST 1" in src and "#define LOL_DIV_PRETEST 1" in src
         for key in ("rgba", "id", "nprimary", "nshadow"):
             assert np.array_equal(a[key], b[key]), key
