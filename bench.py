@@ -249,11 +249,15 @@ def run_reference(args, w, h):
 # --------------------------------------------------------------- FLOP model --
 
 
+# ncu --set full summary of the default scene4 4K launch (tools/ncu_summary.py), committed per round
+NCU_SUMMARY = "r01_v1_final_scene4_4k.txt"
+
+
 def ncu_dram_traffic(args, w, h, world):
     """DRAM bytes of one launch from the committed ncu summary of this very workload, else None."""
     if world != 1 or args.scene != "scene4" or (w, h) != (3840, 2160) or args.workload != "frame":
         return None
-    path = os.path.join(ROOT, "profiles", "r01_v1_boxtest_scene4_4k.txt")  # the kernel as it is benched today
+    path = os.path.join(ROOT, "profiles", NCU_SUMMARY)  # the kernel as it is benched today
     try:
         total, scale = 0.0, {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(path):
@@ -272,7 +276,7 @@ def ncu_hw_flop_frac(args, w, h, world):
     if world != 1 or args.scene != "scene4" or (w, h) != (3840, 2160) or args.workload != "frame":
         return None
     try:
-        for line in open(os.path.join(ROOT, "profiles", "r01_v1_boxtest_scene4_4k.txt")):
+        for line in open(os.path.join(ROOT, "profiles", NCU_SUMMARY)):
             if "hardware FP32 FLOP/cycle" in line:
                 return float(line.split("=")[1].split("%")[0]) / 100.0
     except Exception:
@@ -286,7 +290,7 @@ def ncu_issue_utilisation(args, w, h, world):
     if world != 1 or args.scene != "scene4" or (w, h) != (3840, 2160) or args.workload != "frame":
         return None
     try:
-        for line in open(os.path.join(ROOT, "profiles", "r01_v1_boxtest_scene4_4k.txt")):
+        for line in open(os.path.join(ROOT, "profiles", NCU_SUMMARY)):
             if "SM issue-slot utilisation" in line:
                 return float(line.split("%")[1].split()[0]) / 100.0
     except Exception:
