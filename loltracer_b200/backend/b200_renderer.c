@@ -74,6 +74,8 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 				st->options.shadow_early_out = 0;
 		else if (!strcmp(argv[i], "--variant") && i + 1 < argc)
 			st->options.variant = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--pack-pairs") && i + 1 < argc)
+			st->options.pack_pairs = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc)
 			st->device = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--gpus") && i + 1 < argc)
