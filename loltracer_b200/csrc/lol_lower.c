@@ -1057,7 +1057,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 	struct pairc pc = {0};
 	/* pack_pairs = 1 packs where it was measured to pay: inside table loops (B200, 4K: 1024
 	 * spheres 48.6 -> 45.9 ms, CSG 45.8 -> 43.5 ms).  Straight-line scenes lose a few
-	 * percent (scene4 2.26 -> 2.36 ms with 16 % fewer instructions: the packed instructions
+	 * percent (scene4 2.15 -> 2.26 ms with 13 % fewer instructions: the packed instructions
 	 * keep the FMA pipe as busy as the scalar ones did and their dependent chains issue
 	 * at 0.3-0.45 per clock, profiles/r01_ubench_f32x2.txt), so they pack only on request. */
 	struct cgen g = {.s = s, .out = &body, .fast = fast, .div_ok = div_ok, .two = two, .pack = pack >= 2 ? pack : 0, .pc = &pc,
