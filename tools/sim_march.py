@@ -99,6 +99,8 @@ if MODE == 'shadow':
             tot += np.minimum(T.max(1), K).sum() + np.maximum(T - K, 0).sum() / 32.0
         print(K, tot / base)
     for Kp, Ks in ((32, 16), (48, 24), (64, 32)):
+        print("  rays beyond the cap: primary", float((TP > Kp).mean()), "shadow", float(((T0 > Ks).sum() + (T1 > Ks).sum()) / max(1, (T0 > 0).sum() + (T1 > 0).sum())),
+              " warps with at least one such ray: primary", float((TP.max(1) > Kp).mean()), "shadow", float(((T0.max(1) > Ks).sum() + (T1.max(1) > Ks).sum()) / max(1, (T0.max(1) > 0).sum() + (T1.max(1) > 0).sum())))
         tot = np.minimum(TP.max(1), Kp).sum() + np.maximum(TP - Kp, 0).sum() / 32.0
         for T in (T0, T1):
             tot += np.minimum(T.max(1), Ks).sum() + np.maximum(T - Ks, 0).sum() / 32.0
