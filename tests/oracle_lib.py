@@ -254,3 +254,61 @@ def specialised_sdf(scene, workdir, tag="spec"):
     L.lol_spec_sdf.restype = C.c_float
     port().lolo_set_specialised_sdf(C.cast(L.lol_spec_sdf, C.c_void_p))
     return L
+
+
+# ---- the whole per-pixel pipeline of variant 1, compiled for the host ------------------
+
+PIPELINE_WRAPPER = r"""
+// cb: origin[3] dir[3] right[3] up[3] width height (lolb200_camera_basis)
+extern "C" void lol_host_render(const float* cb, int w, int h, unsigned* rgba, float* dist, unsigned* id,
+                                unsigned short* nprimary, unsigned short* nshadow) {
+  lol_params P;
+  std::memset(&P, 0, sizeof P);
+  P.ox = cb[0]; P.oy = cb[1]; P.oz = cb[2];
+  P.dx = cb[3]; P.dy = cb[4]; P.dz = cb[5];
+  P.rx = cb[6]; P.ry = cb[7]; P.rz = cb[8];
+  P.ux = cb[9]; P.uy = cb[10]; P.uz = cb[11];
+  P.cw = cb[12]; P.ch = cb[13];
+  P.fw = (float)w; P.fh = (float)h; P.w = w; P.h = h; P.world = 1;
+  P.rshift = 16; P.gshift = 8; P.bshift = 0; P.amask = 0xFF000000u;  // XRGB8888, alpha forced
+  lol_host_prologue(P);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      lol_pixel_out o;
+      lol_shade_pixel(P, x, y, o);
+      const size_t i = (size_t)y * w + x;
+      rgba[i] = o.pixel; dist[i] = o.dist; id[i] = o.id;
+      nprimary[i] = (unsigned short)o.n_primary; nshadow[i] = (unsigned short)o.n_shadow;
+    }
+}
+"""
+
+
+def cpu_pipeline(tmp_path, src, tag):
+    """Compiles a generated variant-1 program WHOLE for the host -- helpers, the generated distance code
+    and lol_kernel.cuh's per-pixel pipeline (lol_shade_pixel: camera ray, marches, normal, shadows, Phong,
+    gamma, pack), everything but the kernel around it -- so that kernel-side logic is checked against
+    the oracle without a GPU.  Returns a CDLL with lol_host_render."""
+    import pathlib
+    import subprocess
+    assert "#define LOL_VARIANT 1" in src, "only the phase-sequential pipeline compiles for the host"
+    tmp_path = pathlib.Path(tmp_path)
+    cu = tmp_path / f"pipe_{tag}.cpp"
+    cu.write_text(HOST_SHIM + src + PIPELINE_WRAPPER)
+    so = tmp_path / f"pipe_{tag}.so"
+    subprocess.check_call(["g++", "-O2", "-msse4.2", "-mavx2", "-ffp-contract=off", "-shared", "-fPIC",
+                           "-o", str(so), str(cu)])
+    return C.CDLL(str(so))
+
+
+def cpu_pipeline_render(L, lb, scene, w, h, camera=None):
+    cb = lb.camera_basis(camera or scene.camera, w, h)
+    flat = (C.c_float * 14)(*list(cb.origin), *list(cb.dir), *list(cb.right), *list(cb.up), cb.width, cb.height)
+    rgba = np.zeros((h, w), np.uint32)
+    dist = np.zeros((h, w), np.float32)
+    ids = np.zeros((h, w), np.uint32)
+    npr = np.zeros((h, w), np.uint16)
+    nsh = np.zeros((h, w), np.uint16)
+    L.lol_host_render(flat, w, h, rgba.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p),
+                      ids.ctypes.data_as(C.c_void_p), npr.ctypes.data_as(C.c_void_p), nsh.ctypes.data_as(C.c_void_p))
+    return dict(rgba=rgba, dist=dist, id=ids, nprimary=npr, nshadow=nsh)

@@ -1,0 +1,100 @@
+"""The per-pixel pipeline of the generated program, WITHOUT a GPU: lol_kernel.cuh's lol_shade_pixel
+(variant 1: camera ray, primary march, normal taps, shadow marches, Phong, gamma, pack) is compiled for
+the host together with the generated distance code (tests/oracle_lib.py: cpu_pipeline) and compared with
+the oracle pixel for pixel.  On the host powf is glibc's -- the reference's -- so even RGB is exact here;
+on the GPU the same text runs with CUDA's powf (<= 1/255, tests/test_gpu_parity.py).
+
+What this buys: the kernel-side logic -- the exact skips, the shared first step, the division pre-test,
+packed pairs, table loops -- is checked on every CPU run, and a change to it can be developed without
+GPU time.  What it cannot see: ptxas (contraction, MUFU sequences); that stays with the GPU suite.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import EXAMPLES
+
+
+def _same(got, want, shadow_counts=False):
+    assert np.array_equal(got["id"], want["id"])
+    d, w = got["dist"], want["dist"]
+    assert ((d.view(np.uint32) == w.view(np.uint32)) | (np.isnan(d) & np.isnan(w))).all()
+    assert np.array_equal(got["nprimary"], want["nprimary"])
+    assert np.array_equal(got["rgba"], want["rgba"])  # exact: same libm on both sides
+    if shadow_counts:
+        assert np.array_equal(got["nshadow"], want["nshadow"])
+
+
+OPTIONS = {
+    "default": dict(),
+    "no_skips": dict(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, share_first_step=0),
+    "everything_on": dict(guarded_fastpath=2, pack_pairs=2, share_first_step=2, shadow_div_pretest=1, prune_bounds=2),
+    "ieee_forms": dict(guarded_fastpath=0, prune_bounds=0),
+    "forced_loops": dict(loop_threshold=2, guarded_fastpath=2, share_first_step=2),
+}
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("opts", list(OPTIONS))
+def test_host_compiled_pipeline_equals_oracle(name, opts, scenes_dir, tmp_path):
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, **OPTIONS[opts]))
+    L = ol.cpu_pipeline(tmp_path, src, f"{name}_{opts}")
+    for w, h in ((96, 54), (37, 23)):
+        got = ol.cpu_pipeline_render(L, lb, scene, w, h)
+        want = ol.port_render(scene, w, h, counts=True)
+        # with the skips off the shadow marches take exactly the reference's steps
+        _same(got, want, shadow_counts=(opts == "no_skips"))
+
+
+def test_host_compiled_pipeline_on_the_1024_sphere_scene(tmp_path):
+    """Pruned table loops with hints, Morton groups and packed pairs under the whole pipeline."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    scene = lb.Scene.from_string(scenegen.synthetic_scene_text())
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1))
+    assert "lol_sqrt_fast2(" in src.split("//@@SCENE@@")[0]
+    L = ol.cpu_pipeline(tmp_path, src, "synthetic")
+    w, h = 40, 22
+    _same(ol.cpu_pipeline_render(L, lb, scene, w, h), ol.port_render(scene, w, h, counts=True))
+
+
+@pytest.mark.parametrize("name,point,direction", [
+    ("scene4", (0, 1, -6), (0, 0, -1)),          # at a sphere's centre: sqrt(0), the guard's fallback
+    ("scene4", (3e19, 1, 0), (-1, 0, 0)),        # beyond 2^60
+    ("scene2", (0, 5, -6), (0, -1, 0)),          # cross(dir, up) = 0: a NaN camera basis
+    ("scene", (2, 2, -10), (0, 0, -1)),          # inside the round box: the march ends on step 1
+    ("scene", (-0.0, 0, -0.0), (0, 0, -1)),      # -0 + rd * 0 depends on rd: the shared first step stands aside
+    ("scene4", (-0.0, 6, 3), (0.3, -0.7, -1)),
+])
+def test_host_compiled_pipeline_edge_cameras(name, point, direction, scenes_dir, tmp_path):
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    cam = lb.Camera.make(list(point), list(direction), scene.struct.camera.fov)
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=2, share_first_step=2, shadow_div_pretest=1))
+    L = ol.cpu_pipeline(tmp_path, src, "edge")
+    w, h = 64, 36
+    _same(ol.cpu_pipeline_render(L, lb, scene, w, h, camera=cam), ol.port_render(scene, w, h, camera=cam, counts=True))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_host_compiled_pipeline_on_random_scenes(seed, tmp_path):
+    """Random trees, materials (non-black misses, negative shininess: the skips must switch themselves
+    off), cameras and 0-3 lights through the whole pipeline, straight-line and as forced table loops."""
+    import loltracer_b200 as lb
+    from test_lowering_fuzz import random_scene
+
+    scene = lb.Scene.from_string(random_scene(seed + 300, extensions=False, fixed_head=False))
+    w, h = 48, 27
+    want = ol.port_render(scene, w, h, counts=True)
+    for tag, kw in (("s", dict(guarded_fastpath=2, pack_pairs=2, share_first_step=2, shadow_div_pretest=1)),
+                    ("l", dict(guarded_fastpath=2, loop_threshold=2, prune_bounds=2))):
+        src = lb.lower_cuda(scene, lb.Options.default(variant=1, **kw))
+        L = ol.cpu_pipeline(tmp_path, src, f"fz{seed}{tag}")
+        _same(ol.cpu_pipeline_render(L, lb, scene, w, h), want)
