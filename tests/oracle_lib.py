@@ -271,6 +271,7 @@ extern "C" void lol_host_render(const float* cb, int w, int h, unsigned* rgba, f
   P.cw = cb[12]; P.ch = cb[13];
   P.fw = (float)w; P.fh = (float)h; P.w = w; P.h = h; P.world = 1;
   P.rshift = 16; P.gshift = 8; P.bshift = 0; P.amask = 0xFF000000u;  // XRGB8888, alpha forced
+#if LOL_VARIANT == 1
   lol_host_prologue(P);
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) {
@@ -280,18 +281,32 @@ extern "C" void lol_host_render(const float* cb, int w, int h, unsigned* rgba, f
       rgba[i] = o.pixel; dist[i] = o.dist; id[i] = o.id;
       nprimary[i] = (unsigned short)o.n_primary; nshadow[i] = (unsigned short)o.n_shadow;
     }
+#else  // variant 3: two horizontally adjacent pixels per call, the second one absent at an odd right edge
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; x += 2) {
+      lol_pixel_out o[2];
+      const bool actB = x + 1 < w;
+      lol_shade_pair(P, x, y, actB, o[0], o[1]);
+      for (int k = 0; k < (actB ? 2 : 1); ++k) {
+        const size_t i = (size_t)y * w + x + k;
+        rgba[i] = o[k].pixel; dist[i] = o[k].dist; id[i] = o[k].id;
+        nprimary[i] = (unsigned short)o[k].n_primary; nshadow[i] = (unsigned short)o[k].n_shadow;
+      }
+    }
+#endif
 }
 """
 
 
 def cpu_pipeline(tmp_path, src, tag):
-    """Compiles a generated variant-1 program WHOLE for the host -- helpers, the generated distance code
-    and lol_kernel.cuh's per-pixel pipeline (lol_shade_pixel: camera ray, marches, normal, shadows, Phong,
-    gamma, pack), everything but the kernel around it -- so that kernel-side logic is checked against
-    the oracle without a GPU.  Returns a CDLL with lol_host_render."""
+    """Compiles a generated program (variant 1, or variant 3: two rays per call on the shim's plain pairs)
+    WHOLE for the host -- helpers, the generated distance code and lol_kernel.cuh's per-pixel pipeline
+    (lol_shade_pixel / lol_shade_pair: camera ray, marches, normal, shadows, Phong, gamma, pack), everything
+    but the kernel around it -- so that kernel-side logic is checked against the oracle without a GPU.
+    Returns a CDLL with lol_host_render."""
     import pathlib
     import subprocess
-    assert "#define LOL_VARIANT 1" in src, "only the phase-sequential pipeline compiles for the host"
+    assert "#define LOL_VARIANT 1" in src or "#define LOL_VARIANT 3" in src, "variant 2 lives in shared-memory queues"
     tmp_path = pathlib.Path(tmp_path)
     cu = tmp_path / f"pipe_{tag}.cpp"
     cu.write_text(HOST_SHIM + src + PIPELINE_WRAPPER)

@@ -5,7 +5,7 @@ the oracle pixel for pixel.  On the host powf is glibc's -- the reference's -- s
 on the GPU the same text runs with CUDA's powf (<= 1/255, tests/test_gpu_parity.py).
 
 What this buys: the kernel-side logic -- the exact skips, the shared first step, the division pre-test,
-packed pairs, table loops -- is checked on every CPU run, and a change to it can be developed without
+packed pairs, table loops, the two-ray bookkeeping of variant 3 -- is checked on every CPU run, and a change to it can be developed without
 GPU time.  What it cannot see: ptxas (contraction, MUFU sequences); that stays with the GPU suite.
 """
 import os
@@ -49,6 +49,22 @@ def test_host_compiled_pipeline_equals_oracle(name, opts, scenes_dir, tmp_path):
         want = ol.port_render(scene, w, h, counts=True)
         # with the skips off the shadow marches take exactly the reference's steps
         _same(got, want, shadow_counts=(opts == "no_skips"))
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("loops", [0, 2])
+def test_host_compiled_two_ray_pipeline_equals_oracle(name, loops, scenes_dir, tmp_path):
+    """Variant 3 (lol_shade_pair: two horizontally adjacent pixels per call, a finished ray waiting for
+    its partner) on the shim's plain pairs: every pixel the oracle's, odd widths included (the last
+    pixel of a row has no partner)."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=3, loop_threshold=loops, prune_bounds=2 if loops else 1))
+    assert "#define LOL_VARIANT 3" in src
+    L = ol.cpu_pipeline(tmp_path, src, f"{name}_v3_{loops}")
+    for w, h in ((96, 54), (37, 23)):
+        _same(ol.cpu_pipeline_render(L, lb, scene, w, h), ol.port_render(scene, w, h, counts=True))
 
 
 def test_host_compiled_pipeline_on_the_1024_sphere_scene(tmp_path):
