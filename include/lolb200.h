@@ -168,7 +168,9 @@ typedef struct lolb200_options {
 	int32_t variant;         /* kernel structure: 0 = chosen per scene,
 	                            1 = phase-sequential, 2 = megaloop + lane refill,
 	                            3 = two rays per thread in packed FP32 registers
-	                                (FADD2/FMUL2/FFMA2; needs the guarded forms) */
+	                                (FADD2/FMUL2/FFMA2; needs the guarded forms),
+	                            4 = staged (deferred long rays): lowering only,
+	                                lolb200_renderer_create refuses it            */
 	int32_t loop_threshold;  /* top-level runs of >= this many same-shape
 	                            objects become a loop over __constant__ tables;
 	                            0 = default (16)                                */

@@ -354,6 +354,12 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	else
 		lolb200_options_default(&r->opt);
 	r->scene = lolb200_scene_clone(s);
+	if (r->opt.variant == 4) {
+		/* staged: lol_kernel.cuh has variant 4's per-pixel function (checked on the CPU), not its kernels */
+		lolb200_set_error("kernel variant 4 (deferred long rays) is staged: no device kernel yet");
+		lolb200_renderer_destroy(r);
+		return LOLB200_EINVAL;
+	}
 
 	size_t len = 0;
 	char* src = lolb200_lower_cuda(s, &r->opt, &len);

@@ -1753,7 +1753,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;
 	if (variant == 2 && s->n_objects > 65535u)
 		variant = 1; /* variant 2 keeps object ids in 16 bits */
-	if (variant < 1 || variant > 3) {
+	if (variant < 1 || variant > 4) { /* 4: staged -- its per-pixel function exists, its kernel does not (lol_kernel.cuh) */
 		lolb200_set_error("unknown kernel variant %d", variant);
 		return NULL;
 	}

@@ -259,6 +259,11 @@ def specialised_sdf(scene, workdir, tag="spec"):
 # ---- the whole per-pixel pipeline of variant 1, compiled for the host ------------------
 
 PIPELINE_WRAPPER = r"""
+#include <vector>
+static int lol_host_cap_primary = 256, lol_host_cap_shadow = 128;
+static long lol_host_deferrals = 0;
+extern "C" void lol_host_set_caps(int primary, int shadow) { lol_host_cap_primary = primary; lol_host_cap_shadow = shadow; }
+extern "C" long lol_host_get_deferrals(void) { return lol_host_deferrals; }
 // cb: origin[3] dir[3] right[3] up[3] width height (lolb200_camera_basis)
 extern "C" void lol_host_render(const float* cb, int w, int h, unsigned* rgba, float* dist, unsigned* id,
                                 unsigned short* nprimary, unsigned short* nshadow) {
@@ -281,6 +286,30 @@ extern "C" void lol_host_render(const float* cb, int w, int h, unsigned* rgba, f
       rgba[i] = o.pixel; dist[i] = o.dist; id[i] = o.id;
       nprimary[i] = (unsigned short)o.n_primary; nshadow[i] = (unsigned short)o.n_shadow;
     }
+#elif LOL_VARIANT == 4  // staged: the resumable pipeline -- cap every march, put unfinished pixels aside, resume
+  std::vector<lol_cont> queue;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      lol_cont c;
+      lol_cont_begin(c, x, y);
+      queue.push_back(c);
+    }
+  lol_host_deferrals = 0;
+  while (!queue.empty()) {  // pass after pass, like launch after launch
+    std::vector<lol_cont> next;
+    for (lol_cont& c : queue) {
+      lol_pixel_out o;
+      if (!lol_pixel_run(P, c, o, lol_host_cap_primary, lol_host_cap_shadow)) {
+        next.push_back(c);
+        ++lol_host_deferrals;
+        continue;
+      }
+      const size_t i = (size_t)(c.xy >> 16) * w + (c.xy & 0xffffu);
+      rgba[i] = o.pixel; dist[i] = o.dist; id[i] = o.id;
+      nprimary[i] = (unsigned short)o.n_primary; nshadow[i] = (unsigned short)o.n_shadow;
+    }
+    queue.swap(next);
+  }
 #else  // variant 3: two horizontally adjacent pixels per call, the second one absent at an odd right edge
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; x += 2) {
@@ -306,7 +335,7 @@ def cpu_pipeline(tmp_path, src, tag):
     Returns a CDLL with lol_host_render."""
     import pathlib
     import subprocess
-    assert "#define LOL_VARIANT 1" in src or "#define LOL_VARIANT 3" in src, "variant 2 lives in shared-memory queues"
+    assert "#define LOL_VARIANT 2" not in src, "variant 2 lives in shared-memory queues"
     tmp_path = pathlib.Path(tmp_path)
     cu = tmp_path / f"pipe_{tag}.cpp"
     cu.write_text(HOST_SHIM + src + PIPELINE_WRAPPER)

@@ -114,3 +114,61 @@ def test_host_compiled_pipeline_on_random_scenes(seed, tmp_path):
         src = lb.lower_cuda(scene, lb.Options.default(variant=1, **kw))
         L = ol.cpu_pipeline(tmp_path, src, f"fz{seed}{tag}")
         _same(ol.cpu_pipeline_render(L, lb, scene, w, h), want)
+
+
+# ---- variant 4 (staged): the resumable pipeline behind "deferring long rays" ----------------------
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("opts", ["default", "no_skips", "forced_loops"])
+def test_resumable_pipeline_equals_oracle_at_every_cap(name, opts, scenes_dir, tmp_path):
+    """lol_pixel_run (lol_kernel.cuh, variant 4): every march stops after `cap` evaluations, the pixel goes
+    into a 17-word continuation record and is picked up again in a later pass -- as often as it takes.  At
+    caps 48/24 (the plan), 5/3 and 1/1 (every single evaluation is a resume point: primary march, normal,
+    each light's setup, shadow march, Phong) the frame, distances, ids and step counts are the oracle's,
+    RGB included.  With the skips off the shadow step counts are the reference's too."""
+    import ctypes as C
+
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    kw = dict(OPTIONS[opts])
+    kw.pop("share_first_step", None)  # variant 1's prologue; variant 4 has none yet
+    src = lb.lower_cuda(scene, lb.Options.default(variant=4, **kw))
+    assert "#define LOL_VARIANT 4" in src
+    L = ol.cpu_pipeline(tmp_path, src, f"{name}_v4_{opts}")
+    L.lol_host_get_deferrals.restype = C.c_long
+    w, h = 64, 36
+    want = ol.port_render(scene, w, h, counts=True)
+    seen = []
+    for caps in ((256, 128), (48, 24), (5, 3), (1, 1)):
+        L.lol_host_set_caps(*caps)
+        _same(ol.cpu_pipeline_render(L, lb, scene, w, h), want, shadow_counts=(opts == "no_skips"))
+        seen.append(L.lol_host_get_deferrals())
+    assert seen[0] == 0 and seen[1] > 0 and seen[3] > seen[2] > seen[1]  # the caps did interrupt marches
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_resumable_pipeline_on_random_scenes_and_edge_cameras(seed, tmp_path):
+    import loltracer_b200 as lb
+    from test_lowering_fuzz import random_scene
+
+    scene = lb.Scene.from_string(random_scene(seed + 400, extensions=bool(seed % 2), fixed_head=False))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=4, guarded_fastpath=2, pack_pairs=2))
+    L = ol.cpu_pipeline(tmp_path, src, f"fz4_{seed}")
+    w, h = 40, 22
+    cams = [None, lb.Camera.make([-0.0, 2, 6], [0.1, -0.2, -1], 90), lb.Camera.make([0, 5, -6], [0, -1, 0], 90)]
+    for cam in cams:
+        want = ol.port_render(scene, w, h, camera=cam, counts=True)
+        for caps in ((7, 4), (1, 1)):
+            L.lol_host_set_caps(*caps)
+            _same(ol.cpu_pipeline_render(L, lb, scene, w, h, camera=cam), want)
+
+
+def test_staged_variant_compiles_for_sm_100a(scenes_dir):
+    """Variant 4's device text (the per-pixel function, no kernel yet) goes through NVRTC for sm_100a."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
+    opt = lb.Options.default(variant=4)
+    image = lb.compile_cubin(lb.lower_cuda(scene, opt), opt)
+    assert len(image) > 1000
