@@ -66,4 +66,9 @@ struct lol_doc {
 struct lol_doc* lol_parse_text(const char* text, size_t len, char* err, size_t errlen);
 void lol_doc_free(struct lol_doc* doc);
 
+/* Deepest object nesting the front-end and the lowering accept: both walk the tree
+ * recursively, one frame per level (the reference's bison parser gives up with "memory
+ * exhausted" at YYMAXDEPTH). */
+#define LOLB200_MAX_NESTING 1000
+
 #endif

@@ -13,6 +13,7 @@ int lolb200_scene_check(const lolb200_scene* s);
 /* Scene-dependent licences for the exact work-skipping shortcuts (lol_lower.c). */
 int lolb200_can_skip_black_miss(const lolb200_scene* s);
 int lolb200_can_cull_backfacing(const lolb200_scene* s);
+int lolb200_can_shadow_early(const lolb200_scene* s);
 /* 1 when n*rk corrected by two FMAs equals n/k for every significand of n. */
 int lolb200_div_const_is_exact(float k);
 

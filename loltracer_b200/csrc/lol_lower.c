@@ -13,6 +13,7 @@
 #include "lolb200.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1520,24 +1521,45 @@ static int div_const_proof_soft(float k, float rk) {
 	return 1;
 }
 
+/* The proof walks all 2^23 significands (about 14 ms per distinct k): results are kept for
+ * the life of the process, shared by all threads -- a group of N devices lowers the same
+ * scene N times, and a scene may use any number of distinct smoothness values. */
 int lolb200_div_const_is_exact(float k) {
-	static _Thread_local float cache_k[8];
-	static _Thread_local int cache_ok[8], cache_n;
+	static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+	static struct { uint32_t kbits; int ok; }* cache;
+	static size_t cache_n, cache_cap;
+	const uint32_t kbits = f2u(k);
 	float rk;
-	int ok;
+	int ok = -1;
 	/* k in [2^-20, 2^20]: quotients of in-range numerators neither overflow nor
 	 * lose bits to underflow where 0.5 + q could still notice */
 	if (!(k >= 0x1p-20f && k <= 0x1p20f))
 		return 0;
-	for (int i = 0; i < cache_n; i++)
-		if (f2u(cache_k[i]) == f2u(k))
-			return cache_ok[i];
+	pthread_mutex_lock(&mu);
+	for (size_t i = 0; i < cache_n; i++)
+		if (cache[i].kbits == kbits) {
+			ok = cache[i].ok;
+			break;
+		}
+	pthread_mutex_unlock(&mu);
+	if (ok >= 0)
+		return ok;
 	rk = 1.0f / k;
 	ok = __builtin_cpu_supports("fma") ? div_const_proof_fma(k, rk) : div_const_proof_soft(k, rk);
-	if (cache_n < 8) {
-		cache_k[cache_n] = k;
-		cache_ok[cache_n++] = ok;
+	pthread_mutex_lock(&mu);
+	if (cache_n == cache_cap) {
+		const size_t cap = cache_cap ? cache_cap * 2 : 16;
+		void* grown = realloc(cache, cap * sizeof *cache);
+		if (grown) {
+			cache = grown;
+			cache_cap = cap;
+		}
 	}
+	if (cache_n < cache_cap) {
+		cache[cache_n].kbits = kbits;
+		cache[cache_n++].ok = ok;
+	}
+	pthread_mutex_unlock(&mu);
 	return ok;
 }
 
@@ -1643,6 +1665,31 @@ int lolb200_can_cull_backfacing(const lolb200_scene* s) {
 	for (uint32_t i = 0; i < s->n_materials; i++) {
 		const lolb200_material* m = &s->materials[i];
 		if (!shininess_ok(m) || !finite3(m->diffuse) || !finite3(m->specular))
+			return 0;
+	}
+	return 1;
+}
+
+/* The shadow march may stop once res <= 0 (softshadow then returns maxf(res, 0) = 0) if
+ * nothing can RAISE res afterwards.  res = minf(res, q) only falls while q is ordered; a NaN q
+ * replaces res (MINSS hands back its second operand) and the next ordered q could then lift it
+ * above 0.  q = (50 * d) / t is NaN only for 0/0, inf/inf or a NaN operand.  With every scene
+ * constant and light position finite, sdf() of a finite point is finite (sums of squares, sqrt,
+ * a division by the constant k whose result goes through clamp), so what remains is 0/0, t == 0:
+ *   - t starts at 0 and the first step either leaves the loop (d < 0: q = -inf < -1), makes res
+ *     NaN (d == 0: not <= 0, no early-out), or moves to t = d > 0 with q = +inf;
+ *   - from t > 0 on, a step that does not leave the loop has q >= -1, i.e. d >= -t/50, so
+ *     t + d >= 0.98 t > 0 (for a denormal t the only d in (-t/50, 0) is -0): t stays positive.
+ * Hence at the moment res <= 0 is seen t is positive and finite and stays so: no later q is NaN.
+ * A scene with a non-finite constant, or a NaN camera (then d is NaN, res NaN, never <= 0 -- safe
+ * anyway), is the only way out of this argument, so the licence is per scene like the others. */
+int lolb200_can_shadow_early(const lolb200_scene* s) {
+	for (uint32_t i = 0; i < s->n_lights; i++)
+		if (!finite3(s->lights[i].point))
+			return 0;
+	for (uint32_t i = 0; i < s->n_nodes; i++) {
+		const lolb200_object* o = &s->nodes[i];
+		if (!finite3(o->point) || !finite3(o->point2) || !isfinite(o->radius) || !isfinite(o->smoothness))
 			return 0;
 	}
 	return 1;
@@ -1771,11 +1818,11 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_printf(&out, "#define LOL_EXACT %d\n", o.arith == LOLB200_ARITH_EXACT);
 	sb_printf(&out, "#define LOL_SKIP_MISS %d\n", o.skip_black_miss && lolb200_can_skip_black_miss(s));
 	sb_printf(&out, "#define LOL_CULL %d\n", o.cull_backfacing && lolb200_can_cull_backfacing(s));
-	sb_printf(&out, "#define LOL_SHADOW_EARLY %d\n", o.shadow_early_out != 0);
+	sb_printf(&out, "#define LOL_SHADOW_EARLY %d\n", o.shadow_early_out && lolb200_can_shadow_early(s));
 	sb_printf(&out, "#define LOL_COUNTERS %d\n", o.counters != 0);
 	sb_printf(&out, "#define LOL_VARIANT %d\n", variant);
 	sb_printf(&out, "#define LOL_DIV_PRETEST %d\n", variant == 1 && o.arith == LOLB200_ARITH_EXACT && o.shadow_early_out != 0 &&
-	                                                  o.shadow_div_pretest != 0);
+	                                                  lolb200_can_shadow_early(s) && o.shadow_div_pretest != 0);
 	/* share_first_step = 1: where it was measured to pay (B200, 4K: scene 0.694 -> 0.679 ms, scene4
 	 * 2.149 -> 2.129 ms; scene2 loses 0.8 %, the table-loop scenes more); 2 forces it */
 	sb_printf(&out, "#define LOL_SHARE_FIRST %d\n#define LOL_SDF_FLOPS %lluu\n",

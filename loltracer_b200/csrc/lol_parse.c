@@ -75,7 +75,15 @@ struct parser {
 	char* err;
 	size_t errlen;
 	int failed;
+	int depth;   /* objects open around the current token */
 };
+
+/* An object value nests one level per `type { ... }`.  The reference's bison parser
+ * stops with "memory exhausted" when its stack passes YYMAXDEPTH (10000 symbols, about
+ * six per nesting level); this parser, and the tree walks behind it (build_object, the
+ * lowering's bound_node / emit_node), recurse once per level, so the depth is capped
+ * well inside a default thread stack instead of overflowing it. */
+#define LOL_MAX_NESTING LOLB200_MAX_NESTING
 
 static int is_numch(char c) { return c == '-' || c == '.' || (c >= '0' && c <= '9'); }
 
@@ -234,12 +242,18 @@ static void parse_value(struct parser* p, struct lol_value* v) {
 		} while (accept_punct(p, ','));
 		expect_punct(p, ')');
 	} else if (is_type_tok(p)) {
+		if (p->depth >= LOL_MAX_NESTING) {
+			fail(p, "objects nested deeper than %d levels", LOL_MAX_NESTING);
+			return;
+		}
 		v->kind = LOL_V_OBJ;
 		v->obj = calloc(1, sizeof *v->obj);
 		v->obj->type = p->tokval;
 		next(p);
 		expect_punct(p, '{');
+		p->depth++;
 		parse_deflist(p, v->obj);
+		p->depth--;
 		expect_punct(p, '}');
 	} else {
 		fail(p, "syntax error, expected a value");

@@ -473,6 +473,25 @@ int lolb200_scene_check(const lolb200_scene* s) {
 			return LOLB200_EINVAL;
 		}
 	}
+	if (s->n_nodes) {
+		/* children precede their parents, so one forward pass gives every node's height */
+		uint32_t* height = calloc(s->n_nodes, sizeof *height);
+		int too_deep = 0;
+		for (uint32_t i = 0; i < s->n_nodes && height; i++) {
+			const lolb200_object* o = &s->nodes[i];
+			height[i] = 1;
+			if (LOLB200_OBJ_HAS_CHILDREN(o->type)) {
+				const uint32_t ha = height[o->a], hb = height[o->b];
+				height[i] = 1 + (ha > hb ? ha : hb);
+			}
+			too_deep |= height[i] > LOLB200_MAX_NESTING;
+		}
+		free(height);
+		if (too_deep) {
+			lolb200_set_error("objects nested deeper than %d levels", LOLB200_MAX_NESTING);
+			return LOLB200_EINVAL;
+		}
+	}
 	for (uint32_t i = 0; i < s->n_objects; i++) {
 		if (s->objects[i] >= s->n_nodes) {
 			lolb200_set_error("object %u: node index out of range", i + 1);

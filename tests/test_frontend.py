@@ -115,3 +115,43 @@ def test_camera_basis_matches_reference_ray(scenes_dir):
     assert abs(dot) < 1e-6 and abs(cb.right[1]) < 1e-7
     assert abs(cb.height - math.atan(cam.fov / 2)) < 1e-6
     assert abs(cb.width - cb.height * 320 / 240) < 1e-6
+
+
+def test_deep_nesting_is_a_parse_error_not_a_stack_overflow():
+    """`a = smooth_union { a = smooth_union { ...` recurses once per level in the parser and in
+    every tree walk behind it; the reference's bison parser gives up at YYMAXDEPTH.  Depth is
+    capped (lol_ast.h: LOLB200_MAX_NESTING) and the input is refused with LOLB200_EPARSE."""
+    import loltracer_b200 as lb
+
+    def nested(depth):
+        leaf = "sphere { point = (0,0,-5), radius = 1 }"
+        obj = leaf
+        for _ in range(depth):
+            obj = "smooth_union { smoothness = 0.5, a = %s, b = %s }" % (obj, leaf)
+        return MINI % obj
+
+    ok = lb.Scene.from_string(nested(200))
+    assert ok.struct.n_nodes == 401
+    with pytest.raises(lb.LolB200Error) as e:
+        lb.Scene.from_string(nested(50000))
+    assert e.value.code == -1 and "nested deeper" in str(e.value)
+
+
+def test_many_distinct_smoothness_values_are_each_proved_once():
+    """The division-by-constant proof (2^23 significands per distinct k) is cached for the life
+    of the process, however many distinct k a scene uses: the second lowering costs no proofs."""
+    import time
+
+    import loltracer_b200 as lb
+
+    objs = ", ".join("smooth_union { smoothness = %.3f, a = sphere { point = (%d,0,-8), radius = 1 }, "
+                     "b = sphere { point = (%d,1,-8), radius = 1 } }" % (0.2 + 0.013 * i, i, i) for i in range(24))
+    scene = lb.Scene.from_string(MINI % objs)
+    opt = lb.Options.default(variant=1, guarded_fastpath=2)
+    t0 = time.perf_counter()
+    a = lb.lower_cuda(scene, opt)
+    t1 = time.perf_counter()
+    b = lb.lower_cuda(scene, opt)
+    t2 = time.perf_counter()
+    assert a == b and "#define LOL_DIV_CONST 1" in a
+    assert (t2 - t1) < 0.5 * (t1 - t0) or (t2 - t1) < 0.05

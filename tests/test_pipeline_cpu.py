@@ -172,3 +172,70 @@ def test_staged_variant_compiles_for_sm_100a(scenes_dir):
     opt = lb.Options.default(variant=4)
     image = lb.compile_cubin(lb.lower_cuda(scene, opt), opt)
     assert len(image) > 1000
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_shadow_early_out_with_shadow_origins_inside_objects(seed, tmp_path):
+    """the shadow march's early-out (leave once res <= 0) must not change a pixel even when
+    the shadow ray starts inside or on an object -- negative distances, 0/0 on the first step, res
+    going NaN and coming back.  Crowded scenes: overlapping spheres and boxes as separate top-level
+    objects (a hit point on one is inside its neighbour one unit along the light direction), lights
+    inside objects and on surfaces.  Early-out on, off, and the oracle: the same frame, RGB included
+    (glibc powf on both sides); with it off, the reference's shadow step counts."""
+    import loltracer_b200 as lb
+
+    rng = np.random.default_rng(9100 + seed)
+    objs, centres = [], []
+    for i in range(int(rng.integers(5, 9))):
+        c = rng.uniform(-2.5, 2.5, 3) * [1, 0.4, 1] + [0, 1.2, -6]
+        centres.append(c)
+        m = 1 + i % 2
+        if rng.random() < 0.7:
+            objs.append(f"sphere {{ material = #{m}, point = ({c[0]:.3f},{c[1]:.3f},{c[2]:.3f}), radius = {rng.uniform(1.2, 2.4):.3f} }}")
+        else:
+            e = rng.uniform(0.8, 1.8, 3)
+            objs.append(f"box {{ material = #{m}, point = ({c[0]:.3f},{c[1]:.3f},{c[2]:.3f}), "
+                        f"point2 = ({e[0]:.3f},{e[1]:.3f},{e[2]:.3f}), radius = {rng.uniform(0, 0.4):.3f} }}")
+    objs.append("plane { material = #2, y = -0.5 }")
+    lights = []
+    for k in range(int(rng.integers(1, 4))):
+        if k == 0:      # inside an object
+            p = centres[int(rng.integers(len(centres)))] + rng.uniform(-0.3, 0.3, 3)
+        elif k == 1:    # exactly one unit above the floor: p + dir lands on it for hits below
+            p = np.array([rng.uniform(-3, 3), 0.5, rng.uniform(-8, -4)])
+        else:
+            p = rng.uniform(-6, 6, 3) + [0, 6, -3]
+        lights.append(f"point_light {{ point = ({p[0]:.3f},{p[1]:.3f},{p[2]:.3f}), diffuse_intensity = (2,2,2), "
+                      f"specular_intensity = (1,1,1) }}")
+    text = """materials {
+  { shininess = 0, diffuse = (0,0,0), specular = (0,0,0), ambient = (0,0,0) },
+  { shininess = 8, diffuse = (0.3,0.2,0.1), specular = (0.1,0.1,0.1), ambient = (0.3,0.2,0.1) },
+  { shininess = 2, diffuse = (0.1,0.2,0.3), specular = (0.2,0.1,0.1), ambient = (0.1,0.2,0.3) } }
+scene { ambient { color = (0.05, 0.05, 0.05) }, camera { point = (0, 2.5, 2), direction = (0, -0.25, -1), fov = 90 },
+""" + ",\n".join(lights + objs) + " }"
+    scene = lb.Scene.from_string(text)
+    w, h = 64, 36
+    want = ol.port_render(scene, w, h, counts=True)
+    assert (want["nshadow"] > 0).any()
+    for early in (1, 0):
+        src = lb.lower_cuda(scene, lb.Options.default(variant=1, shadow_early_out=early, cull_backfacing=0))
+        assert f"#define LOL_SHADOW_EARLY {early}" in src
+        L = ol.cpu_pipeline(tmp_path, src, f"se{seed}_{early}")
+        got = ol.cpu_pipeline_render(L, lb, scene, w, h)
+        _same(got, want, shadow_counts=False)
+        if not early:
+            hit = want["id"] != 0
+            assert np.array_equal(got["nshadow"][hit], want["nshadow"][hit])
+
+
+def test_shadow_early_out_is_refused_for_non_finite_scene_constants():
+    """The early-out's proof needs sdf() finite at finite points: a scene with an infinite constant
+    keeps the full march (lolb200_can_shadow_early)."""
+    import loltracer_b200 as lb
+    from test_lowering_fuzz import HEAD
+
+    ok = lb.Scene.from_string(HEAD + "sphere { material = #1, point = (0,1,-5), radius = 1 } }")
+    assert "#define LOL_SHADOW_EARLY 1" in lb.lower_cuda(ok, lb.Options.default(variant=1))
+    s = ok.struct
+    s.nodes[0].radius = float("inf")
+    assert "#define LOL_SHADOW_EARLY 0" in lb.lower_cuda(ok, lb.Options.default(variant=1))
