@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LOLB200_ABI_VERSION 1
+#define LOLB200_ABI_VERSION 2
 
 enum {
 	LOLB200_OK = 0,
@@ -244,6 +244,15 @@ uint64_t lolb200_scene_flops_per_eval(const lolb200_scene* s);
 int lolb200_compile_cubin(const char* cuda_src, const lolb200_options* o,
                           void** image, size_t* image_size, char** log);
 
+/* The jitdump analogues beyond the generated source (tracing_jit_renderer.dasc:424-433,
+ * jitdump.c:93-120): the program's PTX (nvrtcGetPTX for compute_100a) and the SASS listing of a
+ * compiled image (the toolkit's cuobjdump / nvdisasm run on a temporary copy).  Both return
+ * malloc'ed NUL-terminated text (free with lolb200_free).  Host-side phases (lowering, NVRTC,
+ * module load, launches, gathers, read-back) are also bracketed by NVTX ranges named
+ * "lolb200: ..." for timeline profilers. */
+int lolb200_compile_ptx(const char* cuda_src, const lolb200_options* o, char** ptx, size_t* len);
+int lolb200_disassemble(const void* image, size_t image_size, char** sass, size_t* len);
+
 int lolb200_device_count(void);
 
 typedef struct lolb200_renderer lolb200_renderer; /* opaque */
@@ -280,6 +289,16 @@ typedef struct lolb200_shard {
 	int32_t rank, world;
 	int32_t band_rows;      /* multiple of 4; 0 = default (4)                  */
 	int32_t dst_full_frame; /* 0: compact local buffer, 1: full-frame indexing */
+	/* Completion flag of the peer-store gather (optional, NULL = none): a 32-bit word in
+	 * device memory -- typically the CONSUMER's, mapped here through CUDA IPC or peer access --
+	 * that receives done_value (release, system scope) once every pixel store of the launch is
+	 * visible system-wide.  The consumer's stream waits for it with
+	 * lolb200_stream_wait_value32: a stream memory operation over NVLink instead of a
+	 * collective as the "all ranks have stored their bands" barrier.  Use one word per
+	 * producer and a value that grows by one per frame. */
+	void* done_flag;
+	uint32_t done_value;
+	uint32_t reserved;
 } lolb200_shard;
 
 /* Optional per-pixel auxiliaries for parity tests (not part of the product
@@ -290,11 +309,19 @@ typedef struct lolb200_aux {
 	uint32_t* id;
 	uint16_t* primary_steps;
 	uint16_t* shadow_steps;
+	/* launch probes (3 words of device memory, preset to {~0, 0, ~0}): nanoseconds of the GPU's
+	 * global timer at [0] the first moment a warp found the work queue dry, [1] the last warp's
+	 * exit, [2] the first CTA's start.  [1] - [0] is the tail of the launch. */
+	uint64_t* launch_timing;
 } lolb200_aux;
 
 /* The pixel loop of render_thread() (naive_renderer.c:216-236) for one frame or
  * one shard of it, asynchronously on `stream` (a cudaStream_t passed as void*,
- * NULL = default stream).  dst_dev is DEVICE memory, pitch_px in pixels. */
+ * NULL = default stream).  dst_dev is DEVICE memory, pitch_px in pixels.
+ * A renderer has one work queue: launches of one renderer are serialised on the
+ * device (a launch on another stream than the previous one first waits for it),
+ * and calls into one renderer must come from one host thread at a time.  Use one
+ * renderer per stream to overlap frames. */
 int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
                           const lolb200_pixfmt* fmt, const lolb200_shard* shard,
                           void* dst_dev, size_t pitch_px, const lolb200_aux* aux_dev,
@@ -303,9 +330,21 @@ int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* cam, int w,
 /* Same, end to end for a host surface (surf->pixels, surf->pitch in BYTES):
  * uploads the camera, renders on the renderer's device, copies the frame into
  * `pixels` honouring `pitch_bytes`, and returns when the pixels are visible to
- * the host.  This is what b200_renderer.c's frame leader calls. */
+ * the host.  This is what b200_renderer.c's frame leader calls.
+ * The surface belongs to the caller (SDL frees and reallocates a window surface on
+ * resize), so the library never page-locks it behind the owner's back.  On every
+ * call it asks whether `pixels` is page-locked CUDA host memory right now: if so
+ * the copy engine writes straight into it; if not, slabs arrive in a pinned frame
+ * the renderer owns and the calling thread copies them on (overlapped with the
+ * slabs still rendering). */
 int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* cam, int w, int h,
                         const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes);
+
+/* For owners of a surface: page-lock [pixels, pixels + bytes) so that frames are
+ * DMA-ed straight into it (no staging copy).  The range must stay allocated until
+ * lolb200_surface_unpin(pixels); never pin memory somebody else may free. */
+int lolb200_surface_pin(void* pixels, size_t bytes);
+int lolb200_surface_unpin(void* pixels);
 
 /* Sum of the instrumented counters since the last call (options.counters = 1):
  * [0] primary evals, [1] normal-tap evals, [2] shadow evals, [3] pixels,
@@ -341,8 +380,11 @@ size_t lolb200_shard_pixels(int w, int h, int world, int band_rows);
  *                        own bands into the caller's (pinned, portable) surface
  *                        over its own PCIe link -- the fastest way to a frame
  *                        in HOST memory, which is what renderer.h asks for.
- * Calls of one group must come from one thread at a time (the frame leader of
- * b200_renderer.c). */
+ * lolb200_group_render_host drives every device from the calling thread; calls
+ * of it must come from one thread at a time.  A LOLB200_GATHER_HOST frame can also
+ * be driven by several host threads, one SHARE (= one device's bands) each:
+ * this is how main.c's N worker threads (main.c:147-149) each take a GPU in
+ * b200_renderer.c instead of one leader issuing every launch and copy. */
 enum { LOLB200_GATHER_NCCL = 0, LOLB200_GATHER_PEER = 1, LOLB200_GATHER_HOST = 2 };
 typedef struct lolb200_group lolb200_group; /* opaque */
 int lolb200_group_create(const lolb200_scene* s, const lolb200_options* o, const int* devices,
@@ -350,9 +392,24 @@ int lolb200_group_create(const lolb200_scene* s, const lolb200_options* o, const
 void lolb200_group_destroy(lolb200_group* g);
 int lolb200_group_render_host(lolb200_group* g, const lolb200_camera* cam, int w, int h,
                               const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes);
-/* Milliseconds (CUDA events on devices[0]) of the last frame: render + gather,
- * without the copy to the host. */
+/* Share `share` (0 .. lolb200_group_size - 1) of one frame, from launch to its rows in
+ * `pixels`: enqueue returns at once, wait returns when the rows are in host memory.
+ * Different shares may be driven by different threads concurrently (all with the same
+ * camera, size, format and surface); one share by one thread at a time. */
+int lolb200_group_size(const lolb200_group* g);
+int lolb200_group_share_enqueue(lolb200_group* g, int share, const lolb200_camera* cam, int w, int h,
+                                const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes);
+int lolb200_group_share_wait(lolb200_group* g, int share);
+/* Milliseconds (CUDA events on devices[0]) of the last lolb200_group_render_host frame:
+ * render + gather, without the copy to the host. */
 double lolb200_group_last_frame_ms(const lolb200_group* g);
+
+/* Makes `stream` wait (a stream memory operation, no kernel, no host thread) until the 32-bit word
+ * at dev_addr is >= value in the cyclic sense ((int32_t)(*dev_addr - value) >= 0): the consumer's
+ * side of lolb200_shard.done_flag.  lolb200_stream_write_value32 stores a word in stream order
+ * (e.g. to reset the flags). */
+int lolb200_stream_wait_value32(void* stream, void* dev_addr, uint32_t value);
+int lolb200_stream_write_value32(void* stream, void* dev_addr, uint32_t value);
 
 /* CUDA-IPC plumbing for the peer-store variant (render fused with its gather):
  * export a 64-byte handle for a device allocation / map a peer's handle. */

@@ -19,6 +19,8 @@ from .api import (  # noqa: F401
     Shard,
     camera_basis,
     compile_cubin,
+    compile_ptx,
+    disassemble,
     deinterleave,
     device_count,
     lib,
@@ -26,4 +28,8 @@ from .api import (  # noqa: F401
     lower_cuda,
     measure_fp32_peak,
     shard_pixels,
+    stream_wait_value32,
+    stream_write_value32,
+    surface_pin,
+    surface_unpin,
 )

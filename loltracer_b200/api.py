@@ -101,12 +101,13 @@ class PixFmt(C.Structure):
 
 class Shard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("band_rows", C.c_int32),
-                ("dst_full_frame", C.c_int32)]
+                ("dst_full_frame", C.c_int32), ("done_flag", C.c_void_p), ("done_value", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class Aux(C.Structure):
     _fields_ = [("dist", C.c_void_p), ("id", C.c_void_p), ("primary_steps", C.c_void_p),
-                ("shadow_steps", C.c_void_p)]
+                ("shadow_steps", C.c_void_p), ("launch_timing", C.c_void_p)]
 
 
 # -------------------------------------------------------------- library --
@@ -139,6 +140,8 @@ def lib() -> C.CDLL:
         "lolb200_scene_flops_per_eval": (C.c_uint64, [C.POINTER(SceneStruct)]),
         "lolb200_compile_cubin": (i32, [C.c_char_p, C.POINTER(Options), C.POINTER(vp),
                                          C.POINTER(sz), C.POINTER(vp)]),
+        "lolb200_compile_ptx": (i32, [C.c_char_p, C.POINTER(Options), C.POINTER(vp), C.POINTER(sz)]),
+        "lolb200_disassemble": (i32, [C.c_char_p, sz, C.POINTER(vp), C.POINTER(sz)]),
         "lolb200_device_count": (i32, []),
         "lolb200_renderer_create": (i32, [C.POINTER(SceneStruct), C.POINTER(Options), i32,
                                            C.POINTER(vp)]),
@@ -158,6 +161,13 @@ def lib() -> C.CDLL:
         "lolb200_group_destroy": (None, [vp]),
         "lolb200_group_render_host": (i32, [vp, C.POINTER(Camera), i32, i32, C.POINTER(PixFmt), vp, sz]),
         "lolb200_group_last_frame_ms": (C.c_double, [vp]),
+        "lolb200_group_size": (i32, [vp]),
+        "lolb200_group_share_enqueue": (i32, [vp, i32, C.POINTER(Camera), i32, i32, C.POINTER(PixFmt), vp, sz]),
+        "lolb200_group_share_wait": (i32, [vp, i32]),
+        "lolb200_surface_pin": (i32, [vp, sz]),
+        "lolb200_surface_unpin": (i32, [vp]),
+        "lolb200_stream_wait_value32": (i32, [vp, vp, C.c_uint32]),
+        "lolb200_stream_write_value32": (i32, [vp, vp, C.c_uint32]),
         "lolb200_ipc_export": (i32, [vp, C.POINTER(C.c_uint8 * 64)]),
         "lolb200_ipc_open": (i32, [C.POINTER(C.c_uint8 * 64), C.POINTER(vp)]),
         "lolb200_ipc_close": (i32, [vp]),
@@ -255,6 +265,26 @@ def compile_cubin(src: str, options: Optional[Options] = None) -> bytes:
         lib().lolb200_free(img)
 
 
+def compile_ptx(src: str, options: Optional[Options] = None) -> str:
+    """The program's PTX (compute_100a): --dump-ptx of the backend."""
+    out, n = C.c_void_p(), C.c_size_t()
+    _check(lib().lolb200_compile_ptx(src.encode(), C.byref(options) if options else None, C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value).decode()
+    finally:
+        lib().lolb200_free(out)
+
+
+def disassemble(image: bytes) -> str:
+    """SASS listing of a compiled image (cuobjdump / nvdisasm): --dump-sass of the backend."""
+    out, n = C.c_void_p(), C.c_size_t()
+    _check(lib().lolb200_disassemble(image, len(image), C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value).decode(errors="replace")
+    finally:
+        lib().lolb200_free(out)
+
+
 def device_count() -> int:
     return int(lib().lolb200_device_count())
 
@@ -267,6 +297,15 @@ def deinterleave(gathered_ptr: int, frame_ptr: int, w: int, h: int, world: int,
                  shard_px: int, pitch_px: Optional[int] = None, stream: int = 0) -> None:
     _check(lib().lolb200_deinterleave_device(gathered_ptr, frame_ptr, w, h, world, 0, shard_px,
                                              pitch_px or w, stream))
+
+
+def stream_wait_value32(stream: int, dev_addr: int, value: int) -> None:
+    """`stream` waits until the word at dev_addr is >= value (cyclic): a stream memory operation."""
+    _check(lib().lolb200_stream_wait_value32(stream, dev_addr, value & 0xFFFFFFFF))
+
+
+def stream_write_value32(stream: int, dev_addr: int, value: int) -> None:
+    _check(lib().lolb200_stream_write_value32(stream, dev_addr, value & 0xFFFFFFFF))
 
 
 def measure_fp32_peak(device: int = 0, iters: int = 0) -> tuple[float, float]:
@@ -365,9 +404,31 @@ class Group:
                                                pitch_bytes or w * 4))
         return float(lib().lolb200_group_last_frame_ms(self._h))
 
+    @property
+    def size(self) -> int:
+        return int(lib().lolb200_group_size(self._h))
+
+    def share_enqueue(self, share: int, pixels_ptr: int, w: int, h: int, camera: Optional[Camera] = None,
+                      pitch_bytes: Optional[int] = None, fmt: Optional[PixFmt] = None) -> None:
+        """One device's bands of a frame (gather 'host'): asynchronous; any thread may drive a share."""
+        _check(lib().lolb200_group_share_enqueue(self._h, share, C.byref(camera) if camera else None, w, h,
+                                                 C.byref(fmt) if fmt else None, pixels_ptr, pitch_bytes or w * 4))
+
+    def share_wait(self, share: int) -> None:
+        _check(lib().lolb200_group_share_wait(self._h, share))
+
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value and _lib is not None:
             _lib.lolb200_group_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
+
+
+def surface_pin(pixels_ptr: int, nbytes: int) -> None:
+    """Page-lock a surface its caller owns (frames are then DMA-ed straight into it)."""
+    _check(lib().lolb200_surface_pin(pixels_ptr, nbytes))
+
+
+def surface_unpin(pixels_ptr: int) -> None:
+    _check(lib().lolb200_surface_unpin(pixels_ptr))

@@ -13,16 +13,24 @@
  *    frame_entry_barrier and read data->private only after a wake-up.
  *  - Per frame main sets data->surf, zeroes current_line, posts `entry` N times
  *    and waits for N posts on `exit`.  The reference's workers share the frame by
- *    pulling scanlines from current_line (naive_renderer.c:215-216).  A GPU
- *    wants the whole frame in one launch, so the worker that moves current_line
- *    off zero is the frame LEADER: it renders the frame and copies it into
- *    surf->pixels; every other wake-up finds current_line >= height (exactly
- *    what a late worker of the naive renderer sees) and answers at once.  Every
- *    wake-up posts `exit` exactly once, the leader only after the pixels are in
- *    host memory.
+ *    pulling scanlines from current_line (naive_renderer.c:215-216).  Here the
+ *    unit a worker pulls is a GPU's SHARE of the frame, not a scanline:
+ *      one GPU (or an NVLink gather, --gather nccl|peer): one share.  The worker
+ *        that pulls it is the frame leader: it renders the frame and copies it into
+ *        surf->pixels.
+ *      --gpus N --gather host: N shares, share d = the cyclic 4-row bands of GPU d.
+ *        Each worker pulls shares with SDL_AtomicAdd(&current_line, 1) until none
+ *        is left, enqueues the launches and copies of the GPUs it pulled, then waits
+ *        for them: with N workers every GPU has its own host thread issuing its API
+ *        calls (one leader issuing all of them was the limit at 8 GPUs), with fewer
+ *        workers each drives several GPUs, with more the spare ones answer at once.
+ *    A wake-up that finds no share left (exactly what a late worker of the naive
+ *    renderer sees) answers at once.  Every wake-up posts `exit` exactly once, and
+ *    only after the rows it is responsible for are in host memory.
  *  - Flags for the backend sit in argv[3..] (tracing_jit_renderer.dasc:424-428).
  *  - No error channel: message on stderr and exit(1) (main.c:114-118).
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -40,6 +48,12 @@ struct b200_state {
 	int gpus;
 	int gather;
 	int verbose;
+	int shares;          /* units of work per frame pulled through current_line */
+	int pin_surface;     /* --pin-surface: page-lock surf->pixels (see render_prepare) */
+	int wrap_devices;    /* --wrap-devices: --gpus N on fewer GPUs (shares wrap around) */
+	void* pinned;        /* the surface pinned by us */
+	size_t pinned_bytes;
+	pthread_mutex_t pin_lock;
 };
 
 static void b200_die(const char* what) {
@@ -60,9 +74,12 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 	struct b200_state* st = calloc(1, sizeof *st);
 	const char* dump_cuda = NULL;
 	const char* dump_cubin = NULL;
+	const char* dump_ptx = NULL;
+	const char* dump_sass = NULL;
 	lolb200_scene* flat;
 
 	lolb200_options_default(&st->options);
+	pthread_mutex_init(&st->pin_lock, NULL);
 	st->gather = LOLB200_GATHER_HOST;
 	for (int i = 3; i < argc; i++) {
 		if (!strcmp(argv[i], "--exact"))
@@ -91,6 +108,10 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 			dump_cuda = argv[++i];
 		else if (!strcmp(argv[i], "--dump-cubin") && i + 1 < argc)
 			dump_cubin = argv[++i];
+		else if (!strcmp(argv[i], "--dump-ptx") && i + 1 < argc)
+			dump_ptx = argv[++i];
+		else if (!strcmp(argv[i], "--dump-sass") && i + 1 < argc)
+			dump_sass = argv[++i];
 		else if (!strcmp(argv[i], "-j") || !strcmp(argv[i], "--jitdump")) {
 			/* the JIT backend's introspection switch, kept with its meaning:
 			 * leave the generated code where a profiler can find it */
@@ -104,6 +125,17 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 			unsetenv("LOLB200_CACHE_DIR");
 		else if (!strcmp(argv[i], "--verbose"))
 			st->verbose = 1;
+		else if (!strcmp(argv[i], "--wrap-devices"))
+			/* --gpus N with fewer than N GPUs in the box: share i runs on GPU i mod count (for
+			 * trying the N-share protocol on a small box; NCCL refuses a GPU twice) */
+			st->wrap_devices = 1;
+		else if (!strcmp(argv[i], "--pin-surface"))
+			/* Page-lock surf->pixels so that the GPUs' copy engines write straight into it
+			 * (saves the staging copy: matters from about 1080p on).  The surface is SDL's,
+			 * not ours: only for hosts that keep a surface allocated until the frame after
+			 * they stop handing it in (a fixed-size window, the headless host).  Without the
+			 * flag frames go through pinned staging memory the backend owns. */
+			st->pin_surface = 1;
 		/* anything else belongs to someone else (the JIT backend ignores
 		 * unknown flags too) */
 	}
@@ -117,12 +149,16 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 		int devices[64];
 		if (st->gpus > 64)
 			st->gpus = 64;
-		for (int i = 0; i < st->gpus; i++)
+		for (int i = 0; i < st->gpus; i++) {
 			devices[i] = st->device + i;
+			if (st->wrap_devices && lolb200_device_count() > 0)
+				devices[i] %= lolb200_device_count();
+		}
 		if (lolb200_group_create(flat, &st->options, devices, st->gpus, st->gather, &st->group) !=
 		    LOLB200_OK)
 			b200_die("render_prepare");
 	}
+	st->shares = (st->group && st->gather == LOLB200_GATHER_HOST) ? lolb200_group_size(st->group) : 1;
 	/* also built with --gpus N: its source and image are what -j dumps */
 	if (lolb200_renderer_create(flat, &st->options, st->device, &st->renderer) != LOLB200_OK)
 		b200_die("render_prepare");
@@ -137,6 +173,24 @@ void render_prepare(struct render_data* data, int argc, const char* argv[]) {
 		const void* img = lolb200_renderer_image(st->renderer, &n);
 		b200_dump(dump_cubin, img, n);
 	}
+	if (dump_ptx) {
+		char* ptx = NULL;
+		size_t n = 0;
+		if (lolb200_compile_ptx(lolb200_renderer_source(st->renderer), &st->options, &ptx, &n) != LOLB200_OK)
+			b200_die("--dump-ptx");
+		b200_dump(dump_ptx, ptx, n);
+		lolb200_free(ptx);
+	}
+	if (dump_sass) {
+		/* what the GPU executes: the analogue of the JIT's machine code in the jitdump file */
+		size_t n = 0, len = 0;
+		const void* img = lolb200_renderer_image(st->renderer, &n);
+		char* sass = NULL;
+		if (lolb200_disassemble(img, n, &sass, &len) != LOLB200_OK)
+			b200_die("--dump-sass");
+		b200_dump(dump_sass, sass, len);
+		lolb200_free(sass);
+	}
 	if (st->verbose) {
 		int regs = 0, smem = 0, local = 0, threads = 0;
 		lolb200_renderer_kernel_info(st->renderer, &regs, &smem, &local, &threads);
@@ -150,18 +204,17 @@ void render_destroy(struct render_data* data) {
 	struct b200_state* st = data->private;
 	if (!st)
 		return;
+	if (st->pinned)
+		lolb200_surface_unpin(st->pinned);
 	lolb200_group_destroy(st->group);
 	lolb200_renderer_destroy(st->renderer);
 	free(st);
 	data->private = NULL;
 }
 
-static void b200_render_frame(struct render_data* data) {
-	struct b200_state* st = data->private;
-	SDL_Surface* surf = data->surf;
-	const SDL_PixelFormat* f = surf->format;
-	lolb200_camera cam;
-	lolb200_pixfmt fmt;
+/* What every share of a frame needs: the surface's packing and this frame's camera. */
+static void b200_frame_args(struct render_data* data, lolb200_camera* cam, lolb200_pixfmt* fmt) {
+	const SDL_PixelFormat* f = data->surf->format;
 
 	if (f->BytesPerPixel != 4) {
 		/* the reference stores a Uint32 per pixel whatever the format says
@@ -170,23 +223,37 @@ static void b200_render_frame(struct render_data* data) {
 		        f->BytesPerPixel);
 		exit(1);
 	}
-	memset(&fmt, 0, sizeof fmt);
-	fmt.rshift = f->Rshift;
-	fmt.gshift = f->Gshift;
-	fmt.bshift = f->Bshift;
-	fmt.rloss = f->Rloss;
-	fmt.gloss = f->Gloss;
-	fmt.bloss = f->Bloss;
-	fmt.amask = f->Amask;
-	lolb200__camera_out(&data->scene->camera, &cam); /* main.c:180 moves it every frame */
+	memset(fmt, 0, sizeof *fmt);
+	fmt->rshift = f->Rshift;
+	fmt->gshift = f->Gshift;
+	fmt->bshift = f->Bshift;
+	fmt->rloss = f->Rloss;
+	fmt->gloss = f->Gloss;
+	fmt->bloss = f->Bloss;
+	fmt->amask = f->Amask;
+	lolb200__camera_out(&data->scene->camera, cam); /* main.c:180 moves it every frame */
+}
 
-	if (st->group) {
-		if (lolb200_group_render_host(st->group, &cam, surf->w, surf->h, &fmt, surf->pixels,
-		                              (size_t)surf->pitch) != LOLB200_OK)
-			b200_die("render_thread");
-	} else if (lolb200_render_host(st->renderer, &cam, surf->w, surf->h, &fmt, surf->pixels,
-	                               (size_t)surf->pitch) != LOLB200_OK)
-		b200_die("render_thread");
+/* --pin-surface: follow the surface main.c hands in (main.c:182 re-fetches it every frame).
+ * Every worker passes here before it enqueues anything of a frame; the first one to notice a
+ * new surface re-pins it.  At that moment nothing is in flight: main posts a frame's tokens
+ * only after every wake-up of the previous frame has answered (main.c:189-194), and no worker
+ * of this frame enqueues before it has been through this lock. */
+static void b200_follow_surface(struct b200_state* st, SDL_Surface* surf) {
+	const size_t bytes = (size_t)surf->pitch * (size_t)surf->h;
+	if (!st->pin_surface)
+		return;
+	pthread_mutex_lock(&st->pin_lock);
+	if (st->pinned != surf->pixels || st->pinned_bytes != bytes) {
+		if (st->pinned)
+			lolb200_surface_unpin(st->pinned);
+		st->pinned = NULL;
+		if (lolb200_surface_pin(surf->pixels, bytes) == LOLB200_OK) {
+			st->pinned = surf->pixels;
+			st->pinned_bytes = bytes;
+		} /* else: somebody else pinned it, or it cannot be pinned: staging still works */
+	}
+	pthread_mutex_unlock(&st->pin_lock);
 }
 
 int render_thread(void* ptr) {
@@ -197,12 +264,40 @@ int render_thread(void* ptr) {
 		if (SDL_AtomicGet(&exiting))
 			return 0;
 
-		/* Claim all scanlines at once; whoever saw 0 owns the frame.  (A
-		 * minimised window has no rows: claim one anyway so only one thread
-		 * leads, and render nothing.) */
-		int rows = data->surf->h > 0 ? data->surf->h : 1;
-		if (SDL_AtomicAdd(&current_line, rows) == 0 && data->surf->w > 0 && data->surf->h > 0)
-			b200_render_frame(data);
+		struct b200_state* st = data->private;
+		SDL_Surface* surf = data->surf;
+		const int drawable = surf->w > 0 && surf->h > 0; /* a minimised window has no rows */
+		int mine[64], n = 0, share;
+		lolb200_camera cam;
+		lolb200_pixfmt fmt;
+
+		/* Pull shares like the reference pulls scanlines (naive_renderer.c:215-216). */
+		while ((share = SDL_AtomicAdd(&current_line, 1)) < st->shares) {
+			if (!drawable)
+				continue;
+			if (n == 0) {
+				b200_frame_args(data, &cam, &fmt);
+				b200_follow_surface(st, surf);
+			}
+			if (st->shares == 1) {
+				/* the frame leader: one GPU, or an NVLink gather driven by one thread */
+				int rc = st->group
+					? lolb200_group_render_host(st->group, &cam, surf->w, surf->h, &fmt, surf->pixels,
+					                            (size_t)surf->pitch)
+					: lolb200_render_host(st->renderer, &cam, surf->w, surf->h, &fmt, surf->pixels,
+					                      (size_t)surf->pitch);
+				if (rc != LOLB200_OK)
+					b200_die("render_thread");
+				continue;
+			}
+			if (lolb200_group_share_enqueue(st->group, share, &cam, surf->w, surf->h, &fmt, surf->pixels,
+			                                (size_t)surf->pitch) != LOLB200_OK)
+				b200_die("render_thread");
+			mine[n++] = share;
+		}
+		for (int i = 0; i < n; i++)
+			if (lolb200_group_share_wait(st->group, mine[i]) != LOLB200_OK)
+				b200_die("render_thread");
 
 		SDL_SemPost(frame_exit_barrier);
 	}

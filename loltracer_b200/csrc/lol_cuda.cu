@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <nvrtc.h>
+#include <nvtx3/nvToolsExt.h> /* header-only: binds to a profiler's injection library at run time, no link dependency */
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -45,6 +46,17 @@
 	} while (0)
 
 namespace {
+
+/* NVTX ranges around the host-side phases (lower / NVRTC / module load / launch / gather /
+ * read-back): the analogue of the perf jitdump records the reference's JIT writes
+ * (jitdump.c:69-129) -- a timeline tool attributes time to the phase that spent it.  Without a
+ * tool attached a range costs one predictable branch. */
+struct NvtxRange {
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+	NvtxRange(const NvtxRange&) = delete;
+	NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DeviceGuard {
 	int prev = -1;
@@ -87,10 +99,26 @@ struct lolb200_renderer {
 	cudaStream_t copy_stream = nullptr; /* read-back of finished slabs */
 	cudaStream_t slab_stream[LOL_MAX_SLABS] = {}; /* slab k's launch: they may overlap */
 	cudaEvent_t slab_done[LOL_MAX_SLABS] = {};
-	void* registered = nullptr; /* host surface pinned with cudaHostRegister */
-	size_t registered_bytes = 0;
-	void* registered_dev = nullptr; /* device view of the pinned surface (zero-copy) */
-	int host_mode = 0;              /* 0 copy after the kernel, 1 zero-copy stores */
+	/* A host surface that is not CUDA-pinned memory is never registered behind its owner's
+	 * back (the renderer cannot know when SDL or numpy frees it): the read-back lands in
+	 * this pinned frame of our own and the calling thread copies it on. */
+	lol_u32* host_stage = nullptr;
+	size_t host_stage_pixels = 0;
+	cudaEvent_t slab_copied[LOL_MAX_SLABS] = {}; /* slab k has arrived in host memory */
+	/* One launch in flight per work-counter slot: the next launch that uses a slot from a
+	 * different stream waits for this event first (the slot's chunk counter, and for slot 0
+	 * the longest-first buffers, are shared state). */
+	cudaEvent_t slot_done[LOL_MAX_SLABS] = {};
+	void* slot_stream[LOL_MAX_SLABS] = {};
+	bool slot_used[LOL_MAX_SLABS] = {};
+	/* a shard enqueued by host_shard_enqueue and not yet waited for */
+	struct {
+		bool active = false, staged = false;
+		void* pixels = nullptr;
+		size_t pitch_bytes = 0, world = 1, rank = 0, slabs = 0;
+		int w = 0, h = 0;
+		size_t begin[LOL_MAX_SLABS + 1] = {};
+	} pending;
 	/* longest-first chunk order (full-shard launches of lolb200_render_device) */
 	struct {
 		int w = 0, h = 0, rank = -1, world = 0;
@@ -120,6 +148,123 @@ static void write_cache_file(const std::string& path, const void* image, size_t 
 		else
 			remove(tmp);
 	}
+}
+
+/* NVRTC arguments for the arithmetic mode; `arch` is the --gpu-architecture value */
+static std::vector<const char*> nvrtc_args(const lolb200_options& opt, const char* arch) {
+	std::vector<const char*> args = {arch, "--std=c++17", "-lineinfo", "--extra-device-vectorization"};
+	if (opt.arith == LOLB200_ARITH_EXACT) {
+		/* One rounding per operation, IEEE div/sqrt, denormals kept: the
+		 * reference is SSE scalar code without FMA (reference Makefile:3). */
+		args.push_back("--fmad=false");
+		args.push_back("--prec-div=true");
+		args.push_back("--prec-sqrt=true");
+		args.push_back("--ftz=false");
+	} else {
+		args.push_back("--fmad=true");
+		args.push_back("--prec-div=false");
+		args.push_back("--prec-sqrt=false");
+		args.push_back("--ftz=true");
+	}
+	return args;
+}
+
+extern "C" int lolb200_compile_ptx(const char* src, const lolb200_options* o, char** ptx, size_t* len) {
+	lolb200_options opt;
+	if (o)
+		opt = *o;
+	else
+		lolb200_options_default(&opt);
+	if (!src || !ptx) {
+		lolb200_set_error("lolb200_compile_ptx: NULL argument");
+		return LOLB200_EINVAL;
+	}
+	*ptx = nullptr;
+	NvtxRange range("lolb200: NVRTC (PTX)");
+	nvrtcProgram prog;
+	nvrtcResult r = nvrtcCreateProgram(&prog, src, "lol_scene.cu", 0, nullptr, nullptr);
+	if (r != NVRTC_SUCCESS) {
+		lolb200_set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+		return LOLB200_ECOMPILE;
+	}
+	std::vector<const char*> args = nvrtc_args(opt, "--gpu-architecture=compute_100a");
+	r = nvrtcCompileProgram(prog, (int)args.size(), args.data());
+	size_t n = 0;
+	if (r != NVRTC_SUCCESS || nvrtcGetPTXSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
+		size_t log_size = 0;
+		nvrtcGetProgramLogSize(prog, &log_size);
+		std::string text(log_size ? log_size : 1, '\0');
+		if (log_size)
+			nvrtcGetProgramLog(prog, &text[0]);
+		lolb200_set_error("NVRTC (PTX): %s\n%.3500s", nvrtcGetErrorString(r), text.c_str());
+		nvrtcDestroyProgram(&prog);
+		return LOLB200_ECOMPILE;
+	}
+	*ptx = (char*)malloc(n + 1);
+	nvrtcGetPTX(prog, *ptx);
+	(*ptx)[n] = 0;
+	if (len)
+		*len = strlen(*ptx);
+	nvrtcDestroyProgram(&prog);
+	return LOLB200_OK;
+}
+
+/* SASS listing of a compiled image.  Disassembly is a toolkit TOOL, not a library: the image goes to a
+ * temporary file and cuobjdump -sass (else nvdisasm) runs on it -- from $LOLB200_DISASSEMBLER, PATH,
+ * $CUDA_HOME/bin or /usr/local/cuda/bin. */
+extern "C" int lolb200_disassemble(const void* image, size_t size, char** sass, size_t* len) {
+	if (!image || !size || !sass) {
+		lolb200_set_error("lolb200_disassemble: NULL argument");
+		return LOLB200_EINVAL;
+	}
+	*sass = nullptr;
+	char path[] = "/tmp/lolb200-XXXXXX.cubin";
+	const int fd = mkstemps(path, 6);
+	if (fd < 0 || write(fd, image, size) != (ssize_t)size) {
+		lolb200_set_error("lolb200_disassemble: cannot write %s", path);
+		if (fd >= 0) {
+			close(fd);
+			unlink(path);
+		}
+		return LOLB200_EINVAL;
+	}
+	close(fd);
+	std::vector<std::string> tools;
+	if (const char* t = getenv("LOLB200_DISASSEMBLER"))
+		tools.push_back(t);
+	tools.push_back("cuobjdump -sass");
+	if (const char* home = getenv("CUDA_HOME"))
+		tools.push_back(std::string(home) + "/bin/cuobjdump -sass");
+	tools.push_back("/usr/local/cuda/bin/cuobjdump -sass");
+	tools.push_back("nvdisasm -c");
+	tools.push_back("/usr/local/cuda/bin/nvdisasm -c");
+	std::string text;
+	for (const std::string& tool : tools) {
+		const std::string cmd = tool + " " + path + " 2>/dev/null";
+		FILE* p = popen(cmd.c_str(), "r");
+		if (!p)
+			continue;
+		text.clear();
+		char buf[8192];
+		size_t got;
+		while ((got = fread(buf, 1, sizeof buf, p)) > 0)
+			text.append(buf, got);
+		const int rc = pclose(p);
+		if (rc == 0 && text.find("lol_render") != std::string::npos)
+			break;
+		text.clear();
+	}
+	unlink(path);
+	if (text.empty()) {
+		lolb200_set_error("lolb200_disassemble: no working cuobjdump / nvdisasm (PATH, $CUDA_HOME/bin, "
+		                  "/usr/local/cuda/bin, or set LOLB200_DISASSEMBLER)");
+		return LOLB200_EINVAL;
+	}
+	*sass = (char*)malloc(text.size() + 1);
+	memcpy(*sass, text.c_str(), text.size() + 1);
+	if (len)
+		*len = text.size();
+	return LOLB200_OK;
 }
 
 extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, void** image,
@@ -220,22 +365,11 @@ extern "C" int lolb200_compile_cubin(const char* src, const lolb200_options* o, 
 		lolb200_set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
 		return LOLB200_ECOMPILE;
 	}
-	std::vector<const char*> args = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
-	                                 "--extra-device-vectorization"};
-	if (opt.arith == LOLB200_ARITH_EXACT) {
-		/* One rounding per operation, IEEE div/sqrt, denormals kept: the
-		 * reference is SSE scalar code without FMA (reference Makefile:3). */
-		args.push_back("--fmad=false");
-		args.push_back("--prec-div=true");
-		args.push_back("--prec-sqrt=true");
-		args.push_back("--ftz=false");
-	} else {
-		args.push_back("--fmad=true");
-		args.push_back("--prec-div=false");
-		args.push_back("--prec-sqrt=false");
-		args.push_back("--ftz=true");
+	std::vector<const char*> args = nvrtc_args(opt, "--gpu-architecture=sm_100a");
+	{
+		NvtxRange range("lolb200: NVRTC (sm_100a)");
+		r = nvrtcCompileProgram(prog, (int)args.size(), args.data());
 	}
-	r = nvrtcCompileProgram(prog, (int)args.size(), args.data());
 	size_t log_size = 0;
 	nvrtcGetProgramLogSize(prog, &log_size);
 	std::string text(log_size ? log_size : 1, '\0');
@@ -309,11 +443,17 @@ extern "C" void lolb200_renderer_destroy(lolb200_renderer* r) {
 		for (cudaEvent_t e : r->slab_done)
 			if (e)
 				cudaEventDestroy(e);
+		for (cudaEvent_t e : r->slab_copied)
+			if (e)
+				cudaEventDestroy(e);
+		for (cudaEvent_t e : r->slot_done)
+			if (e)
+				cudaEventDestroy(e);
+		if (r->host_stage)
+			cudaFreeHost(r->host_stage);
 		for (cudaStream_t st : r->slab_stream)
 			if (st)
 				cudaStreamDestroy(st);
-		if (r->registered)
-			cudaHostUnregister(r->registered);
 		cudaFree(r->frame);
 		cudaFree(r->counter);
 		cudaFree(r->stats);
@@ -362,7 +502,9 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	}
 
 	size_t len = 0;
+	nvtxRangePushA("lolb200: lower scene to CUDA C");
 	char* src = lolb200_lower_cuda(s, &r->opt, &len);
+	nvtxRangePop();
 	if (!src) {
 		lolb200_renderer_destroy(r);
 		return LOLB200_EINVAL;
@@ -400,6 +542,7 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 		return LOLB200_ENODEVICE;
 	}
 	r->sm_count = prop.multiProcessorCount;
+	NvtxRange load_range("lolb200: load module");
 	CREATE_TRY(cudaLibraryLoadData(&r->lib, r->image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 	CREATE_TRY(cudaLibraryGetKernel(&r->kernel, r->lib, "lol_render"));
 	{
@@ -444,6 +587,10 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	CREATE_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : r->slab_done)
+		CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	for (cudaEvent_t& e : r->slab_copied)
+		CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	for (cudaEvent_t& e : r->slot_done)
 		CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreate(&r->t_begin));
 	CREATE_TRY(cudaEventCreate(&r->t_end));
@@ -584,7 +731,7 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 		lolb200_set_error("lolb200_render_device: bad argument");
 		return LOLB200_EINVAL;
 	}
-	lolb200_shard sh = {0, 1, LOL_BAND_ROWS, 1};
+	lolb200_shard sh = {0, 1, LOL_BAND_ROWS, 1, nullptr, 0u, 0u};
 	if (shard)
 		sh = *shard;
 	if (sh.band_rows == 0)
@@ -643,11 +790,19 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 		P.aux_id = aux->id;
 		P.aux_primary = aux->primary_steps;
 		P.aux_shadow = aux->shadow_steps;
+		P.timing = (lol_u64*)aux->launch_timing;
 	}
+	P.done_flag = (lol_u32*)sh.done_flag;
+	P.done_value = sh.done_value;
 	P.stats = r->stats;
 
 	DeviceGuard g(r->device);
-	/* a whole shard in one launch: chunks are pulled longest first */
+	/* a whole shard in one launch: chunks are pulled longest first.  (lpt_prepare may enqueue on
+	 * `stream`: the slot's previous launch, if it came from another stream, goes first.) */
+	if (counter_slot == 0 && r->slot_used[0] && r->slot_stream[0] != stream) {
+		CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, r->slot_done[0], 0));
+		r->slot_stream[0] = stream; /* ordered now */
+	}
 	const bool lpt = band_begin == 0 && band_count == 0 && counter_slot == 0 && lpt_prepare(r, P, stream);
 	if (lpt) {
 		P.cost = r->lpt.cost;
@@ -658,11 +813,18 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 	const size_t grid_needed = (warps_needed + r->threads / 32 - 1) / (r->threads / 32);
 	if (grid > grid_needed)
 		grid = grid_needed;
+	/* the slot's previous launch came from another stream: it must have left the counter
+	 * (and the longest-first buffers) before this one starts */
+	if (r->slot_used[counter_slot] && r->slot_stream[counter_slot] != stream)
+		CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, r->slot_done[counter_slot], 0));
 	void* args[] = {&P};
 	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3((unsigned)r->threads),
 	                          args, r->dyn_smem, (cudaStream_t)stream));
 	if (lpt)
 		lpt_after_launch(r, stream);
+	CUDA_TRY(cudaEventRecord(r->slot_done[counter_slot], (cudaStream_t)stream));
+	r->slot_stream[counter_slot] = stream;
+	r->slot_used[counter_slot] = true;
 	return LOLB200_OK;
 }
 
@@ -670,42 +832,73 @@ extern "C" int lolb200_render_device(lolb200_renderer* r, const lolb200_camera* 
                                      const lolb200_pixfmt* fmt, const lolb200_shard* shard,
                                      void* dst_dev, size_t pitch_px, const lolb200_aux* aux,
                                      void* stream) {
+	NvtxRange range("lolb200: launch lol_render");
 	return launch_bands(r, cam, w, h, fmt, shard, dst_dev, pitch_px, aux, stream, 0, 0, 0);
 }
 
-/* Pin the caller's surface once (SDL hands back the same pixels until the
- * window is resized) so the read-back is DMA at PCIe speed.  Portable: every
- * device of an in-process group copies into the same surface.  A surface that
- * somebody else already pinned (the group, or another renderer of this process)
- * is used as it is. */
-static void pin_surface(lolb200_renderer* r, void* pixels, size_t bytes) {
-	if (r->registered == pixels && r->registered_bytes == bytes)
+/* ------------------------------------------------------------ host surfaces -- */
+
+/* Is [pixels, pixels + bytes) page-locked CUDA host memory RIGHT NOW (cudaHostAlloc, or
+ * cudaHostRegister / lolb200_surface_pin by its owner)?  Asked on every frame and never
+ * cached: the renderer does not own the surface, so yesterday's answer says nothing about
+ * a buffer that was freed and another that now lives at the same address.  *dev_view is
+ * the device-side address for zero-copy stores (NULL when the memory is not mapped). */
+static bool surface_is_pinned(void* pixels, size_t bytes, void** dev_view) {
+	if (dev_view)
+		*dev_view = nullptr;
+	cudaPointerAttributes first, last;
+	if (cudaPointerGetAttributes(&first, pixels) != cudaSuccess ||
+	    cudaPointerGetAttributes(&last, (char*)pixels + (bytes ? bytes - 1 : 0)) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	if (first.type != cudaMemoryTypeHost || last.type != cudaMemoryTypeHost)
+		return false;
+	if (dev_view && cudaHostGetDevicePointer(dev_view, pixels, 0) != cudaSuccess) {
+		cudaGetLastError();
+		*dev_view = nullptr;
+	}
+	return true;
+}
+
+/* The owner of a surface may page-lock it so that frames are DMA-ed straight into it; the
+ * range must stay allocated until lolb200_surface_unpin. */
+extern "C" int lolb200_surface_pin(void* pixels, size_t bytes) {
+	if (!pixels || !bytes) {
+		lolb200_set_error("lolb200_surface_pin: bad argument");
+		return LOLB200_EINVAL;
+	}
+	CUDA_TRY(cudaHostRegister(pixels, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_surface_unpin(void* pixels) {
+	CUDA_TRY(cudaHostUnregister(pixels));
+	return LOLB200_OK;
+}
+
+/* the renderer's own pinned frame for surfaces that are plain pageable memory */
+static int stage_reserve(lolb200_renderer* r, size_t pixels) {
+	if (r->host_stage_pixels >= pixels)
+		return LOLB200_OK;
+	if (r->host_stage)
+		cudaFreeHost(r->host_stage);
+	r->host_stage = nullptr;
+	r->host_stage_pixels = 0;
+	CUDA_TRY(cudaHostAlloc(&r->host_stage, pixels * sizeof(lol_u32), cudaHostAllocPortable));
+	r->host_stage_pixels = pixels;
+	return LOLB200_OK;
+}
+
+/* rows [y0, y0 + rows) of a compact w-pixel-wide frame into a surface with its own pitch */
+static void copy_rows(void* pixels, size_t pitch_bytes, size_t y0, const lol_u32* src, size_t w, size_t rows) {
+	char* dst = (char*)pixels + y0 * pitch_bytes;
+	if (pitch_bytes == w * 4) {
+		memcpy(dst, src, rows * w * 4);
 		return;
-	if (r->registered) {
-		cudaHostUnregister(r->registered);
-		r->registered = nullptr;
 	}
-	r->registered_dev = nullptr;
-	r->registered_bytes = 0;
-	cudaPointerAttributes attr;
-	if (cudaPointerGetAttributes(&attr, pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
-		if (cudaHostGetDevicePointer(&r->registered_dev, pixels, 0) != cudaSuccess) {
-			cudaGetLastError();
-			r->registered_dev = nullptr;
-		}
-		return; /* pinned by someone else: not ours to unregister */
-	}
-	cudaGetLastError();
-	if (cudaHostRegister(pixels, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess) {
-		r->registered = pixels;
-		r->registered_bytes = bytes;
-		if (cudaHostGetDevicePointer(&r->registered_dev, pixels, 0) != cudaSuccess) {
-			cudaGetLastError();
-			r->registered_dev = nullptr;
-		}
-	} else {
-		cudaGetLastError(); /* pageable copy still works, only slower */
-	}
+	for (size_t y = 0; y < rows; ++y)
+		memcpy(dst + y * pitch_bytes, src + y * w, w * 4);
 }
 
 /* Slab boundaries for the render / read-back pipeline.  Equal slabs when the copy
@@ -742,6 +935,7 @@ extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* ca
 		lolb200_set_error("lolb200_render_host: bad argument");
 		return LOLB200_EINVAL;
 	}
+	NvtxRange range("lolb200: frame to host surface (slabs: render + D2H)");
 	DeviceGuard g(r->device);
 	const size_t need = (size_t)w * h;
 	if (r->frame_pixels < need) {
@@ -751,21 +945,29 @@ extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* ca
 		CUDA_TRY(cudaMalloc(&r->frame, need * sizeof(lol_u32)));
 		r->frame_pixels = need;
 	}
-	pin_surface(r, pixels, pitch_bytes * (size_t)h);
+	void* dev_view = nullptr;
+	const bool pinned = surface_is_pinned(pixels, pitch_bytes * (size_t)(h - 1) + (size_t)w * 4, &dev_view);
 	const char* mode = getenv("LOLB200_HOST_MODE");
-	if (mode && !strcmp(mode, "mapped") && r->registered_dev && pitch_bytes % 4 == 0) {
+	if (mode && !strcmp(mode, "mapped") && pinned && dev_view && pitch_bytes % 4 == 0) {
 		/* zero-copy: the kernel stores pixels straight into the pinned surface */
-		int rc0 = lolb200_render_device(r, cam, w, h, fmt, nullptr, r->registered_dev, pitch_bytes / 4,
+		int rc0 = lolb200_render_device(r, cam, w, h, fmt, nullptr, dev_view, pitch_bytes / 4,
 		                                nullptr, r->stream);
 		if (rc0 != LOLB200_OK)
 			return rc0;
 		CUDA_TRY(cudaStreamSynchronize(r->stream));
 		return LOLB200_OK;
 	}
+	if (!pinned) {
+		int rc0 = stage_reserve(r, need);
+		if (rc0 != LOLB200_OK)
+			return rc0;
+	}
 	/* The frame is rendered as a few slabs of bands, one launch each; while slab
 	 * k+1 renders, the copy engine moves slab k into the caller's surface, so the
 	 * frame costs about max(kernel, PCIe copy) plus one slab's copy instead of
-	 * their sum.  LOLB200_HOST_MODE=copy renders and copies the frame whole. */
+	 * their sum.  LOLB200_HOST_MODE=copy renders and copies the frame whole.
+	 * A pageable surface receives each slab from the renderer's pinned frame as soon
+	 * as the slab has arrived there (memcpy by this thread, overlapping later slabs). */
 	const size_t bands = ((size_t)h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
 	size_t slabs = (mode && !strcmp(mode, "copy")) ? 1 : LOL_MAX_SLABS;
 	if (mode && !strncmp(mode, "slabs", 5) && atoi(mode + 5) > 0)
@@ -790,11 +992,25 @@ extern "C" int lolb200_render_host(lolb200_renderer* r, const lolb200_camera* ca
 			return rc;
 		CUDA_TRY(cudaEventRecord(r->slab_done[k], r->slab_stream[k]));
 		CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->slab_done[k], 0));
-		CUDA_TRY(cudaMemcpy2DAsync((char*)pixels + y0 * pitch_bytes, pitch_bytes, r->frame + y0 * w,
-		                           (size_t)w * 4, (size_t)w * 4, rows, cudaMemcpyDeviceToHost,
-		                           r->copy_stream));
+		if (pinned) {
+			CUDA_TRY(cudaMemcpy2DAsync((char*)pixels + y0 * pitch_bytes, pitch_bytes, r->frame + y0 * w,
+			                           (size_t)w * 4, (size_t)w * 4, rows, cudaMemcpyDeviceToHost,
+			                           r->copy_stream));
+		} else {
+			CUDA_TRY(cudaMemcpyAsync(r->host_stage + y0 * w, r->frame + y0 * w, rows * (size_t)w * 4,
+			                         cudaMemcpyDeviceToHost, r->copy_stream));
+			CUDA_TRY(cudaEventRecord(r->slab_copied[k], r->copy_stream));
+		}
 	}
 	CUDA_TRY(cudaEventRecord(r->t_end, r->slab_stream[last_k]));
+	if (!pinned) {
+		for (size_t k = 0; k <= last_k; ++k) {
+			const size_t y0 = begin[k] * LOL_BAND_ROWS;
+			const size_t y1 = begin[k + 1] * LOL_BAND_ROWS < (size_t)h ? begin[k + 1] * LOL_BAND_ROWS : (size_t)h;
+			CUDA_TRY(cudaEventSynchronize(r->slab_copied[k]));
+			copy_rows(pixels, pitch_bytes, y0, r->host_stage + y0 * w, (size_t)w, y1 - y0);
+		}
+	}
 	CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
 	if (cudaEventSynchronize(r->t_end) == cudaSuccess &&
 	    cudaEventElapsedTime(&r->last_render_ms, r->t_begin, r->t_end) == cudaSuccess)
@@ -819,6 +1035,7 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 		lolb200_set_error("lolb200_render_host_shard: bad argument");
 		return LOLB200_EINVAL;
 	}
+	NvtxRange range("lolb200: enqueue shard (render + D2H of own bands)");
 	DeviceGuard g(r->device);
 	const size_t world = (size_t)shard->world, rank = (size_t)shard->rank;
 	const size_t need = lolb200_shard_pixels(w, h, shard->world, 0);
@@ -829,7 +1046,13 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 		CUDA_TRY(cudaMalloc(&r->frame, need * sizeof(lol_u32)));
 		r->frame_pixels = need;
 	}
-	pin_surface(r, pixels, pitch_bytes * (size_t)h);
+	const bool pinned = surface_is_pinned(pixels, pitch_bytes * (size_t)(h - 1) + (size_t)w * 4, nullptr);
+	if (!pinned) {
+		int rc0 = stage_reserve(r, need);
+		if (rc0 != LOLB200_OK)
+			return rc0;
+	}
+	r->pending.active = false;
 	const size_t bands = ((size_t)h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
 	const size_t local_bands = bands > rank ? (bands - rank + world - 1) / world : 0;
 	if (local_bands == 0)
@@ -838,11 +1061,11 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 	sh.band_rows = LOL_BAND_ROWS;
 	sh.dst_full_frame = 0;
 	/* fewer slabs as the shard shrinks: with eight ranks the copy is a quarter of
-	 * the kernel and every slab costs the (single) leader thread API calls */
+	 * the kernel and every slab costs its host thread API calls */
 	size_t slabs = LOL_MAX_SLABS / world >= 2 ? LOL_MAX_SLABS / world : 2;
 	if (local_bands < slabs * 16)
 		slabs = local_bands / 16 ? local_bands / 16 : 1;
-	size_t begin[LOL_MAX_SLABS + 1];
+	size_t* begin = r->pending.begin;
 	slab_plan(local_bands, slabs, false, begin);
 	/* whole bands with rows back to back in the surface: one copy per slab */
 	const bool one_copy = pitch_bytes == (size_t)w * 4 && h % LOL_BAND_ROWS == 0;
@@ -856,6 +1079,15 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 			return rc;
 		CUDA_TRY(cudaEventRecord(r->slab_done[k], r->slab_stream[k]));
 		CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->slab_done[k], 0));
+		if (!pinned) {
+			/* pageable surface: the compact slab goes to our pinned frame; host_shard_wait hands
+			 * the bands on */
+			const size_t off = b0 * LOL_BAND_ROWS * (size_t)w;
+			CUDA_TRY(cudaMemcpyAsync(r->host_stage + off, r->frame + off, nb * LOL_BAND_ROWS * (size_t)w * 4,
+			                         cudaMemcpyDeviceToHost, r->copy_stream));
+			CUDA_TRY(cudaEventRecord(r->slab_copied[k], r->copy_stream));
+			continue;
+		}
 		if (one_copy) {
 			const size_t y0 = (b0 * world + rank) * LOL_BAND_ROWS;
 			CUDA_TRY(cudaMemcpy2DAsync((char*)pixels + y0 * pitch_bytes, world * LOL_BAND_ROWS * pitch_bytes,
@@ -882,11 +1114,36 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 			                           cudaMemcpyDeviceToHost, r->copy_stream));
 		}
 	}
+	r->pending.active = true;
+	r->pending.staged = !pinned;
+	r->pending.pixels = pixels;
+	r->pending.pitch_bytes = pitch_bytes;
+	r->pending.world = world;
+	r->pending.rank = rank;
+	r->pending.slabs = slabs;
+	r->pending.w = w;
+	r->pending.h = h;
 	return LOLB200_OK;
 }
 
 static int host_shard_wait(lolb200_renderer* r) {
+	NvtxRange range("lolb200: wait for shard in host memory");
 	DeviceGuard g(r->device);
+	auto& q = r->pending;
+	if (q.active && q.staged) {
+		const size_t bands = ((size_t)q.h + LOL_BAND_ROWS - 1) / LOL_BAND_ROWS;
+		const size_t local_bands = bands > q.rank ? (bands - q.rank + q.world - 1) / q.world : 0;
+		for (size_t k = 0; k < q.slabs && q.begin[k] < local_bands; ++k) {
+			CUDA_TRY(cudaEventSynchronize(r->slab_copied[k]));
+			for (size_t lb = q.begin[k]; lb < q.begin[k + 1]; ++lb) {
+				const size_t y0 = (lb * q.world + q.rank) * LOL_BAND_ROWS;
+				const size_t rows = y0 + LOL_BAND_ROWS <= (size_t)q.h ? LOL_BAND_ROWS : (size_t)q.h - y0;
+				copy_rows(q.pixels, q.pitch_bytes, y0, r->host_stage + lb * LOL_BAND_ROWS * (size_t)q.w,
+				          (size_t)q.w, rows);
+			}
+		}
+	}
+	q.active = false;
 	CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
 	return LOLB200_OK;
 }
@@ -956,6 +1213,50 @@ extern "C" int lolb200_deinterleave_device(const void* gathered, void* frame, in
 	lol_deinterleave_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
 		(const lol_u32*)gathered, (lol_u32*)frame, w, h, world, shard_pixels, pitch_px, vec);
 	CUDA_TRY(cudaGetLastError());
+	return LOLB200_OK;
+}
+
+/* ------------------------------------------------- stream memory operations -- */
+
+/* Driver entry points are looked up at run time (cudaGetDriverEntryPoint): the library has no
+ * link-time dependency on libcuda and still loads on a box without a driver. */
+typedef int (*lol_stream_value32_fn)(void* stream, unsigned long long addr, unsigned int value, unsigned int flags);
+
+static lol_stream_value32_fn driver_entry(const char* name) {
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return (lol_stream_value32_fn)fn;
+}
+
+extern "C" int lolb200_stream_wait_value32(void* stream, void* dev_addr, uint32_t value) {
+	static lol_stream_value32_fn fn = driver_entry("cuStreamWaitValue32");
+	if (!fn) {
+		lolb200_set_error("cuStreamWaitValue32 is not available from this driver");
+		return LOLB200_ECUDA;
+	}
+	const int rc = fn(stream, (unsigned long long)(uintptr_t)dev_addr, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+	if (rc != 0) {
+		lolb200_set_error("cuStreamWaitValue32 failed: CUresult %d", rc);
+		return LOLB200_ECUDA;
+	}
+	return LOLB200_OK;
+}
+
+extern "C" int lolb200_stream_write_value32(void* stream, void* dev_addr, uint32_t value) {
+	static lol_stream_value32_fn fn = driver_entry("cuStreamWriteValue32");
+	if (!fn) {
+		lolb200_set_error("cuStreamWriteValue32 is not available from this driver");
+		return LOLB200_ECUDA;
+	}
+	const int rc = fn(stream, (unsigned long long)(uintptr_t)dev_addr, value, 0x0 /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+	if (rc != 0) {
+		lolb200_set_error("cuStreamWriteValue32 failed: CUresult %d", rc);
+		return LOLB200_ECUDA;
+	}
 	return LOLB200_OK;
 }
 
@@ -1102,8 +1403,8 @@ struct lolb200_group {
 	int w = 0, h = 0;
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	double last_ms = 0.0;
-	void* registered = nullptr;
-	size_t registered_bytes = 0;
+	lol_u32* host_stage = nullptr; /* pinned, ours: the way to a pageable surface (nccl / peer gathers) */
+	size_t host_stage_px = 0;
 };
 
 #define NCCL_TRY(expr)                                                                   \
@@ -1136,8 +1437,8 @@ extern "C" void lolb200_group_destroy(lolb200_group* g) {
 	}
 	if (!g->devices.empty()) {
 		cudaSetDevice(g->devices[0]);
-		if (g->registered)
-			cudaHostUnregister(g->registered);
+		if (g->host_stage)
+			cudaFreeHost(g->host_stage);
 		cudaFree(g->gathered);
 		cudaFree(g->frame);
 		if (g->t0)
@@ -1199,6 +1500,8 @@ extern "C" int lolb200_group_create(const lolb200_scene* s, const lolb200_option
 	if (n > 1 && gather == LOLB200_GATHER_PEER) {
 		for (int i = 1; i < n; ++i) {
 			int can = 0;
+			if (g->devices[i] == g->devices[0])
+				continue; /* the same device twice (tests on a one-GPU box): its own memory */
 			cudaDeviceCanAccessPeer(&can, g->devices[i], g->devices[0]);
 			if (!can) {
 				lolb200_set_error("device %d cannot store into device %d (no peer access)",
@@ -1244,6 +1547,30 @@ static int group_resize(lolb200_group* g, int w, int h) {
 	return LOLB200_OK;
 }
 
+extern "C" int lolb200_group_size(const lolb200_group* g) { return g ? g->n : 0; }
+
+/* Share i of a frame = devices[i]'s bands, from launch to surf->pixels.  enqueue returns at
+ * once, wait returns when the rows are in host memory.  Different shares may be driven by
+ * different host threads at the same time (every share has its own renderer, streams and
+ * staging); this is how main.c's worker threads each take a GPU. */
+extern "C" int lolb200_group_share_enqueue(lolb200_group* g, int share, const lolb200_camera* cam, int w, int h,
+                                           const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes) {
+	if (!g || share < 0 || share >= g->n || g->gather != LOLB200_GATHER_HOST) {
+		lolb200_set_error("lolb200_group_share_enqueue: bad argument (shares exist for LOLB200_GATHER_HOST groups)");
+		return LOLB200_EINVAL;
+	}
+	lolb200_shard sh = {share, g->n, 0, 0, nullptr, 0u, 0u};
+	return host_shard_enqueue(g->renderers[share], cam, w, h, fmt, &sh, pixels, pitch_bytes, nullptr);
+}
+
+extern "C" int lolb200_group_share_wait(lolb200_group* g, int share) {
+	if (!g || share < 0 || share >= g->n) {
+		lolb200_set_error("lolb200_group_share_wait: bad argument");
+		return LOLB200_EINVAL;
+	}
+	return host_shard_wait(g->renderers[share]);
+}
+
 extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera* cam, int w, int h,
                                          const lolb200_pixfmt* fmt, void* pixels, size_t pitch_bytes) {
 	if (!g || !pixels || w <= 0 || h <= 0 || pitch_bytes < (size_t)w * 4) {
@@ -1253,24 +1580,12 @@ extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera*
 	if (g->n == 1)
 		return lolb200_render_host(g->renderers[0], cam, w, h, fmt, pixels, pitch_bytes);
 	cudaSetDevice(g->devices[0]);
-	const size_t bytes = pitch_bytes * (size_t)h;
-	if (g->registered != pixels || g->registered_bytes != bytes) {
-		if (g->registered)
-			cudaHostUnregister(g->registered);
-		g->registered = nullptr;
-		if (cudaHostRegister(pixels, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
-			g->registered = pixels;
-			g->registered_bytes = bytes;
-		} else {
-			cudaGetLastError();
-		}
-	}
 	if (g->gather == LOLB200_GATHER_HOST) {
 		/* every GPU renders its bands and copies them into the surface over its own
 		 * PCIe link; nothing crosses NVLink */
 		CUDA_TRY(cudaEventRecord(g->t0, g->streams[0]));
 		for (int i = 0; i < g->n; ++i) {
-			lolb200_shard sh = {i, g->n, 0, 0};
+			lolb200_shard sh = {i, g->n, 0, 0, nullptr, 0u, 0u};
 			int rc = host_shard_enqueue(g->renderers[i], cam, w, h, fmt, &sh, pixels, pitch_bytes,
 			                            i ? g->t0 : nullptr);
 			if (rc != LOLB200_OK)
@@ -1295,7 +1610,7 @@ extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera*
 	cudaSetDevice(g->devices[0]);
 	CUDA_TRY(cudaEventRecord(g->t0, g->streams[0]));
 	for (int i = 0; i < g->n; ++i) {
-		lolb200_shard sh = {i, g->n, 0, g->gather == LOLB200_GATHER_PEER ? 1 : 0};
+		lolb200_shard sh = {i, g->n, 0, g->gather == LOLB200_GATHER_PEER ? 1 : 0, nullptr, 0u, 0u};
 		if (i > 0) {
 			/* rank i starts after devices[0]'s t0 so the timing brackets all ranks */
 			cudaSetDevice(g->devices[i]);
@@ -1308,6 +1623,7 @@ extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera*
 			return rc;
 	}
 	if (g->gather == LOLB200_GATHER_NCCL) {
+		NvtxRange range("lolb200: NCCL gather + de-interleave");
 		NCCL_TRY(g_nccl.GroupStart());
 		for (int i = 1; i < g->n; ++i) {
 			NCCL_TRY(g_nccl.Send(g->shard[i], g->shard_px, ncclInt32, 0, g->comms[i], g->streams[i]));
@@ -1332,9 +1648,24 @@ extern "C" int lolb200_group_render_host(lolb200_group* g, const lolb200_camera*
 	}
 	cudaSetDevice(g->devices[0]);
 	CUDA_TRY(cudaEventRecord(g->t1, g->streams[0]));
-	CUDA_TRY(cudaMemcpy2DAsync(pixels, pitch_bytes, g->frame, (size_t)w * 4, (size_t)w * 4, (size_t)h,
-	                           cudaMemcpyDeviceToHost, g->streams[0]));
-	CUDA_TRY(cudaStreamSynchronize(g->streams[0]));
+	if (surface_is_pinned(pixels, pitch_bytes * (size_t)(h - 1) + (size_t)w * 4, nullptr)) {
+		CUDA_TRY(cudaMemcpy2DAsync(pixels, pitch_bytes, g->frame, (size_t)w * 4, (size_t)w * 4, (size_t)h,
+		                           cudaMemcpyDeviceToHost, g->streams[0]));
+		CUDA_TRY(cudaStreamSynchronize(g->streams[0]));
+	} else {
+		/* a pageable surface is not ours to register: through the group's own pinned frame */
+		if (g->host_stage_px < (size_t)w * h) {
+			if (g->host_stage)
+				cudaFreeHost(g->host_stage);
+			g->host_stage = nullptr;
+			g->host_stage_px = 0;
+			CUDA_TRY(cudaHostAlloc(&g->host_stage, (size_t)w * h * sizeof(lol_u32), cudaHostAllocPortable));
+			g->host_stage_px = (size_t)w * h;
+		}
+		CUDA_TRY(cudaMemcpyAsync(g->host_stage, g->frame, (size_t)w * h * 4, cudaMemcpyDeviceToHost, g->streams[0]));
+		CUDA_TRY(cudaStreamSynchronize(g->streams[0]));
+		copy_rows(pixels, pitch_bytes, 0, g->host_stage, (size_t)w, (size_t)h);
+	}
 	float ms = 0.f;
 	if (cudaEventElapsedTime(&ms, g->t0, g->t1) == cudaSuccess)
 		g->last_ms = ms;

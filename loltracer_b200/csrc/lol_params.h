@@ -36,6 +36,9 @@ struct lol_params {
 	lol_u64* stats;      // LOL_COUNTERS: 8 accumulators
 	const lol_u32* order; // optional: n-th pull from the queue -> chunk (longest first)
 	lol_u32* cost;        // optional: clocks each chunk took, by chunk
+	lol_u64* timing;      // optional probes: [0] queue dry, [1] last exit, [2] first start (global timer, ns)
+	lol_u32* done_flag;   // optional: word (any GPU's memory) that receives done_value when the launch is complete
+	lol_u32 done_value;
 };
 
 #define LOL_BAND_ROWS 4

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(raw, s), f"{s} declared in lolb200.h but not exported"
-    assert lb.lib().lolb200_abi_version() == 1
+    assert lb.lib().lolb200_abi_version() == 2
 
 
 def test_bindings_cover_the_header():
@@ -34,17 +34,31 @@ def test_bindings_cover_the_header():
         assert getattr(L, s).argtypes is not None, f"no ctypes signature for {s}"
 
 
-def test_struct_layouts_match_c():
-    """sizeof of the PODs as the C compiler sees them (checked through the parser)."""
+def test_struct_layouts_match_c(tmp_path):
+    """sizeof of every POD and the offset of its last field, as gcc sees include/lolb200.h, against the
+    ctypes mirrors in loltracer_b200/api.py."""
+    import subprocess
+
     from loltracer_b200 import api
 
-    assert C.sizeof(api.Material) == 40
-    assert C.sizeof(api.Light) == 36
-    assert C.sizeof(api.Object) == 48
-    assert C.sizeof(api.Camera) == 28
-    assert C.sizeof(api.Options) == 64
-    assert C.sizeof(api.PixFmt) == 12
-    assert C.sizeof(api.Shard) == 16
+    pods = {"lolb200_material": (api.Material, "ambient"), "lolb200_light": (api.Light, "specular_intensity"),
+            "lolb200_object": (api.Object, "b"), "lolb200_camera": (api.Camera, "fov"),
+            "lolb200_scene": (api.SceneStruct, "camera"), "lolb200_camera_basis": (api.CameraBasis, "height"),
+            "lolb200_options": (api.Options, "shadow_div_pretest"), "lolb200_pixfmt": (api.PixFmt, "amask"),
+            "lolb200_shard": (api.Shard, "done_value"), "lolb200_aux": (api.Aux, "launch_timing")}
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lolb200.h"\nint main(void) {\n' + "".join(
+        f'  printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {last}));\n'
+        for name, (_, last) in pods.items()) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    seen = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        name, size, off = line.split()
+        seen[name] = (int(size), int(off))
+    for name, (cls, last) in pods.items():
+        assert seen[name] == (C.sizeof(cls), getattr(cls, last).offset), name
+    assert C.sizeof(api.Options) == 64 and C.sizeof(api.Shard) == 32
 
 
 def test_no_cpu_fallback(scenes_dir):
@@ -77,3 +91,32 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r"oracle_lib|liblol_oracle|liblolref|lolo_render|lolref_", text):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_ptx_and_sass_dumps_work_without_a_gpu(scenes_dir):
+    """--dump-ptx / --dump-sass (the jitdump analogue): the program's PTX targets sm_100a
+    and carries the kernel; the SASS listing of the compiled image comes from the toolkit's
+    disassembler and shows the FP32 pipeline the kernel is made of."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
+    opt = lb.Options.default()
+    src = lb.lower_cuda(scene, opt)
+    ptx = lb.compile_ptx(src, opt)
+    assert ".target sm_100a" in ptx and ".entry lol_render" in ptx
+    assert "fma.rn.f32" in ptx and "mul.rn.f32" in ptx       # the guarded forms' explicit FMAs, plain products
+    sass = lb.disassemble(lb.compile_cubin(src, opt))
+    assert "lol_render" in sass and "FADD" in sass and "MUFU.RSQ" in sass
+    assert "HMMA" not in sass and "UTCMMA" not in sass         # no tensor-core instruction: FP32 ALU work
+
+
+def test_library_has_no_link_time_dependency_on_the_driver_or_nvtx():
+    """libcuda (stream memory operations) and a profiler's NVTX injection library are bound at run
+    time, NCCL through dlopen: the library loads on a box that has none of them."""
+    import subprocess
+
+    import loltracer_b200 as lb
+
+    needed = subprocess.check_output(["readelf", "-d", lb.library_path()], text=True)
+    libs = re.findall(r"NEEDED.*\[(.*?)\]", needed)
+    assert not [x for x in libs if x.startswith(("libcuda.so", "libnccl", "libnvToolsExt"))], libs

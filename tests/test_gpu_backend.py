@@ -93,6 +93,71 @@ def test_group_api_matches_single_gpu(scenes_dir):
     r.close()
 
 
+@pytest.mark.parametrize("threads,gpus", [(1, 4), (3, 2), (8, 2), (2, 5)])
+@pytest.mark.parametrize("pin", [False, True])
+def test_worker_threads_pull_gpu_shares(threads, gpus, pin, scenes_dir, tmp_path):
+    """main.c's N worker threads each take a GPU's share of the frame (b200_renderer.c: shares are
+    pulled through current_line like scanlines): fewer threads than GPUs, more threads than GPUs,
+    pageable and pinned surfaces -- the same frame as one GPU.  --wrap-devices lets the N-share
+    protocol run on a box with fewer GPUs (share i on GPU i mod count), so this runs everywhere."""
+    if not os.path.exists(HOST):
+        pytest.skip("headless host not built")
+    w, h = 1283, 721
+    path = os.path.join(scenes_dir, "scene4.lol")
+    one = tmp_path / "one.bin"
+    out = subprocess.run([HOST, "2", path, "--size", f"{w}x{h}", "--frames", "2", "--raw", str(one)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    raw = tmp_path / "many.bin"
+    cmd = [HOST, str(threads), path, "--size", f"{w}x{h}", "--frames", "4", "--warmup", "1", "--gpus", str(gpus),
+           "--gather", "host", "--wrap-devices", "--raw", str(raw)] + (["--pin-surface"] if pin else [])
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert np.array_equal(np.fromfile(raw, np.uint32), np.fromfile(one, np.uint32))
+
+
+def test_group_shares_driven_by_threads_and_resizes(scenes_dir):
+    """lolb200_group_share_enqueue / _wait: every share of a frame driven by its own host thread,
+    frame after frame with the surface changing size in between; equals the single-GPU frame.
+    Two shares on ONE device when the box has a single GPU."""
+    import threading
+
+    import loltracer_b200 as lb
+
+    n = max(2, lb.device_count())
+    devices = [i % lb.device_count() for i in range(n)]
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene3.lol"))
+    r = lb.Renderer(scene)
+    g = lb.Group(scene, n, "host", devices=devices)
+    assert g.size == n
+    for (w, h) in [(1000, 563), (320, 240), (1000, 563), (37, 9)]:
+        one = np.zeros((h, w), np.uint32)
+        r.render_host(one.ctypes.data, w, h)
+        got = np.zeros((h, w), np.uint32)
+        errors = []
+
+        def drive(share):
+            try:
+                g.share_enqueue(share, got.ctypes.data, w, h)
+                g.share_wait(share)
+            except Exception as e:  # surfaced below
+                errors.append(e)
+
+        ts = [threading.Thread(target=drive, args=(i,)) for i in range(n)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errors, errors
+        assert np.array_equal(got, one), (w, h)
+        # and the one-thread entry point over the same group
+        got[:] = 0
+        g.render_host(got.ctypes.data, w, h)
+        assert np.array_equal(got, one), (w, h)
+    g.close()
+    r.close()
+
+
 @pytest.mark.gpu
 def test_staged_variant_is_refused_on_the_device():
     """Variant 4 (deferred long rays) has a CPU-checked per-pixel function and no kernel yet: the device
