@@ -169,8 +169,11 @@ typedef struct lolb200_options {
 	                            1 = phase-sequential, 2 = megaloop + lane refill,
 	                            3 = two rays per thread in packed FP32 registers
 	                                (FADD2/FMUL2/FFMA2; needs the guarded forms),
-	                            4 = staged (deferred long rays): lowering only,
-	                                lolb200_renderer_create refuses it            */
+	                            4 = deferred long rays: a march that is not over
+	                                after defer_cap_* evaluations puts its pixel
+	                                aside in a global queue; a second launch
+	                                (lol_resume) finishes those pixels, one per
+	                                lane (exact: same operations per ray)         */
 	int32_t loop_threshold;  /* top-level runs of >= this many same-shape
 	                            objects become a loop over __constant__ tables;
 	                            0 = default (16)                                */
@@ -218,6 +221,8 @@ typedef struct lolb200_options {
 	                            Measured slower on B200 (scene4 4K 2.149 -> 2.171
 	                            ms: the divergent branch costs more than the six
 	                            divisions in seven it saves), so off by default    */
+	int32_t defer_cap_primary;  /* variant 4: evaluations of a primary / shadow march  */
+	int32_t defer_cap_shadow;   /* before the pixel is put aside; 0 = default (48, 24) */
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

@@ -90,6 +90,10 @@ struct lolb200_renderer {
 	int variant = 1;
 	int threads = LOLB200_KERNEL_THREADS; /* CTA size the program was generated for */
 	size_t dyn_smem = 0; /* variant 2: warp-private queues */
+	cudaKernel_t resume_kernel = nullptr; /* variant 4: lol_resume */
+	lol_u32* queue = nullptr;     /* variant 4: continuation records of all slots, SoA per slot partition */
+	size_t queue_slots = 0;       /* per work-counter slot */
+	lol_u32* queue_ctl = nullptr; /* per slot: [0] pushed, [1] next to resume, [2] finished CTAs (+ pad) */
 	lol_u32* counter = nullptr; /* device: [0] next chunk, [1] finished CTAs */
 	lol_u64* stats = nullptr;   /* device: 8 accumulators (options.counters) */
 	/* render_host staging */
@@ -455,6 +459,8 @@ extern "C" void lolb200_renderer_destroy(lolb200_renderer* r) {
 			if (st)
 				cudaStreamDestroy(st);
 		cudaFree(r->frame);
+		cudaFree(r->queue);
+		cudaFree(r->queue_ctl);
 		cudaFree(r->counter);
 		cudaFree(r->stats);
 		if (r->lib)
@@ -494,12 +500,6 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	else
 		lolb200_options_default(&r->opt);
 	r->scene = lolb200_scene_clone(s);
-	if (r->opt.variant == 4) {
-		/* staged: lol_kernel.cuh has variant 4's per-pixel function (checked on the CPU), not its kernels */
-		lolb200_set_error("kernel variant 4 (deferred long rays) is staged: no device kernel yet");
-		lolb200_renderer_destroy(r);
-		return LOLB200_EINVAL;
-	}
 
 	size_t len = 0;
 	nvtxRangePushA("lolb200: lower scene to CUDA C");
@@ -545,6 +545,11 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	NvtxRange load_range("lolb200: load module");
 	CREATE_TRY(cudaLibraryLoadData(&r->lib, r->image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 	CREATE_TRY(cudaLibraryGetKernel(&r->kernel, r->lib, "lol_render"));
+	if (strstr(r->source.c_str(), "#define LOL_VARIANT 4")) {
+		CREATE_TRY(cudaLibraryGetKernel(&r->resume_kernel, r->lib, "lol_resume"));
+		CREATE_TRY(cudaMalloc(&r->queue_ctl, 4 * LOL_MAX_SLABS * sizeof(lol_u32)));
+		CREATE_TRY(cudaMemset(r->queue_ctl, 0, 4 * LOL_MAX_SLABS * sizeof(lol_u32)));
+	}
 	{
 		/* the lowering states what it generated */
 		const char* v = strstr(r->source.c_str(), "#define LOL_VARIANT ");
@@ -560,6 +565,10 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 			CREATE_TRY(cudaFuncSetAttribute((const void*)r->kernel,
 			                                cudaFuncAttributeMaxDynamicSharedMemorySize,
 			                                (int)r->dyn_smem));
+			if (r->resume_kernel)
+				CREATE_TRY(cudaFuncSetAttribute((const void*)r->resume_kernel,
+				                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+				                                (int)r->dyn_smem));
 		}
 		if (r->variant == 2 && sm) {
 			r->dyn_smem = (size_t)atol(sm + strlen("#define LOL_SMEM_PER_WARP ")) *
@@ -813,11 +822,46 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 	const size_t grid_needed = (warps_needed + r->threads / 32 - 1) / (r->threads / 32);
 	if (grid > grid_needed)
 		grid = grid_needed;
+	if (r->resume_kernel) {
+		/* Variant 4: room for a quarter of the launch's pixels in the continuation queue (17 words per
+		 * record); when it overflows, lanes finish their pixels in place.  One partition per
+		 * work-counter slot, so slab launches do not share a queue. */
+		const size_t px = (size_t)P.n_chunks * P.chunk_w * LOL_BAND_ROWS;
+		size_t want = px / 4 < 65536 ? 65536 : px / 4;
+		if (const char* e = getenv("LOLB200_DEFER_QUEUE")) /* tests: a tiny queue exercises the overflow path */
+			if (atol(e) > 0)
+				want = (size_t)atol(e);
+		want = (want + 31) & ~(size_t)31;
+		if (r->queue_slots < want) {
+			CUDA_TRY(cudaDeviceSynchronize()); /* no launch may still use the old queue */
+			cudaFree(r->queue);
+			r->queue = nullptr;
+			r->queue_slots = 0;
+			CUDA_TRY(cudaMalloc(&r->queue, want * 17 * sizeof(lol_u32) * LOL_MAX_SLABS));
+			r->queue_slots = want;
+		}
+		P.q = r->queue + (size_t)counter_slot * r->queue_slots * 17;
+		P.q_cap = (lol_u32)r->queue_slots;
+		P.q_ctl = r->queue_ctl + 4 * counter_slot;
+		P.cap_primary = r->opt.defer_cap_primary > 0 ? (lol_u32)r->opt.defer_cap_primary : 48u;
+		P.cap_shadow = r->opt.defer_cap_shadow > 0 ? (lol_u32)r->opt.defer_cap_shadow : 24u;
+	}
 	/* the slot's previous launch came from another stream: it must have left the counter
 	 * (and the longest-first buffers) before this one starts */
 	if (r->slot_used[counter_slot] && r->slot_stream[counter_slot] != stream)
 		CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, r->slot_done[counter_slot], 0));
 	void* args[] = {&P};
+	if (r->resume_kernel) {
+		/* the completion flag (if any) belongs to the LAST launch of the pair */
+		lol_params first = P;
+		first.done_flag = nullptr;
+		void* first_args[] = {&first};
+		CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3((unsigned)r->threads),
+		                          first_args, r->dyn_smem, (cudaStream_t)stream));
+		P.timing = nullptr;
+		CUDA_TRY(cudaLaunchKernel((const void*)r->resume_kernel, dim3((unsigned)((size_t)r->sm_count * r->blocks_per_sm)),
+		                          dim3((unsigned)r->threads), args, r->dyn_smem, (cudaStream_t)stream));
+	} else
 	CUDA_TRY(cudaLaunchKernel((const void*)r->kernel, dim3((unsigned)grid), dim3((unsigned)r->threads),
 	                          args, r->dyn_smem, (cudaStream_t)stream));
 	if (lpt)

@@ -1800,7 +1800,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;
 	if (variant == 2 && s->n_objects > 65535u)
 		variant = 1; /* variant 2 keeps object ids in 16 bits */
-	if (variant < 1 || variant > 4) { /* 4: staged -- its per-pixel function exists, its kernel does not (lol_kernel.cuh) */
+	if (variant < 1 || variant > 4) {
 		lolb200_set_error("unknown kernel variant %d", variant);
 		return NULL;
 	}
@@ -1842,7 +1842,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		 * scene4 and a quarter of the warps is gone (measured 2.39 vs 2.30 ms) */
 		const int min_blocks = o.min_blocks > 0 ? o.min_blocks
 		                       : (variant == 3 && threads == 128) ? 5
-		                       : (variant == 1 && threads == 256) ? 4 : 0;
+		                       : ((variant == 1 || variant == 4) && threads == 256) ? 4 : 0;
 		sb_printf(&out, "#define LOL_THREADS %d\n", threads);
 		if (min_blocks)
 			sb_printf(&out, "#define LOL_LAUNCH_BOUNDS __launch_bounds__(%d, %d)\n", threads, min_blocks);

@@ -39,6 +39,11 @@ struct lol_params {
 	lol_u64* timing;      // optional probes: [0] queue dry, [1] last exit, [2] first start (global timer, ns)
 	lol_u32* done_flag;   // optional: word (any GPU's memory) that receives done_value when the launch is complete
 	lol_u32 done_value;
+	// variant 4 (deferred long rays): a march that is not over after cap_* evaluations puts its pixel aside
+	lol_u32 cap_primary, cap_shadow;
+	lol_u32 q_cap;        // slots in the continuation queue
+	lol_u32* q;           // records, structure of arrays: word f of slot s at q[f * q_cap + s]
+	lol_u32* q_ctl;       // [0] records pushed, [1] next record to resume, [2] finished CTAs of lol_resume
 };
 
 #define LOL_BAND_ROWS 4

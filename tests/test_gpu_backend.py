@@ -156,15 +156,3 @@ def test_group_shares_driven_by_threads_and_resizes(scenes_dir):
         assert np.array_equal(got, one), (w, h)
     g.close()
     r.close()
-
-
-@pytest.mark.gpu
-def test_staged_variant_is_refused_on_the_device():
-    """Variant 4 (deferred long rays) has a CPU-checked per-pixel function and no kernel yet: the device
-    layer says so instead of loading a program without lol_render."""
-    import loltracer_b200 as lb
-
-    scene = lb.Scene.from_file(os.path.join(ROOT, "tests", "golden", "scenes", "scene.lol"))
-    with pytest.raises(lb.LolB200Error) as e:
-        lb.Renderer(scene, lb.Options.default(variant=4))
-    assert "staged" in str(e.value)

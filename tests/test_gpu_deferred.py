@@ -1,0 +1,135 @@
+"""Variant 4 (deferred long rays: lol_render with march caps + a continuation queue, lol_resume) against
+variant 1 and the oracle.  What a ray computes is variant 1's, operation for operation; only when and in which
+warp it computes changes -- so everything compared here is compared for EQUALITY."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import EXAMPLES
+from test_gpu_parity import _check, _render
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _scene(lb, name, scenes_dir):
+    from loltracer_b200 import scenegen
+
+    if name.startswith("synthetic"):
+        return lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name.endswith("csg")))
+    return lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+
+
+def _same(a, b):
+    for key in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", EXAMPLES + ["synthetic"])
+@pytest.mark.parametrize("caps", [(24, 12), (48, 24)])
+def test_deferred_rays_4k_bit_identical_to_variant1(name, caps, scenes_dir):
+    """3840x2160, all four examples and the 1024-sphere scene (C4), caps 24/12 and 48/24: the SAME frame,
+    distances, ids, primary and shadow step counts and evaluation counters as variant 1."""
+    import loltracer_b200 as lb
+
+    w, h = 3840, 2160
+    scene = _scene(lb, name, scenes_dir)
+    a = _render(lb, scene, w, h, options=lb.Options.default(variant=1, counters=1, share_first_step=0))
+    b = _render(lb, scene, w, h, options=lb.Options.default(variant=4, counters=1, defer_cap_primary=caps[0],
+                                                            defer_cap_shadow=caps[1]))
+    assert "#define LOL_VARIANT 4" in b["renderer"].source
+    _same(a, b)
+    ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
+    assert ca == cb, (ca, cb)
+    a["renderer"].close()
+    b["renderer"].close()
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_deferred_rays_match_the_oracle(name, scenes_dir):
+    import loltracer_b200 as lb
+
+    w, h = 1001, 562
+    scene = _scene(lb, name, scenes_dir)
+    want = ol.port_render(scene, w, h, counts=True)
+    for caps in ((48, 24), (5, 3), (1, 1)):  # at 1/1 every evaluation of every march is a resume point
+        got = _render(lb, scene, w, h, options=lb.Options.default(variant=4, defer_cap_primary=caps[0],
+                                                                  defer_cap_shadow=caps[1]))
+        _check(got, want)
+        assert np.array_equal(got["nprimary"], want["nprimary"])
+        got["renderer"].close()
+
+
+def test_deferred_rays_with_the_skips_off_march_the_references_steps(scenes_dir):
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, "scene4", scenes_dir)
+    w, h = 400, 226
+    opt = lb.Options.default(variant=4, skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, counters=1,
+                             defer_cap_primary=16, defer_cap_shadow=8)
+    got = _render(lb, scene, w, h, options=opt)
+    want = ol.port_render(scene, w, h, counts=True)
+    _check(got, want)
+    assert np.array_equal(got["nshadow"], want["nshadow"])
+    c, t = got["renderer"].read_counters(), want["totals"]
+    assert (c["primary_evals"], c["normal_evals"], c["shadow_evals"]) == (t["primary"], t["normal"], t["shadow"])
+
+
+def test_a_full_queue_costs_time_not_pixels(scenes_dir, monkeypatch):
+    """When the continuation queue is full a lane keeps marching in place: with a queue of 64 records for a
+    1080p frame almost every deferral overflows, and the frame is still variant 1's."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, "scene4", scenes_dir)
+    w, h = 1920, 1080
+    a = _render(lb, scene, w, h, options=lb.Options.default(variant=1))
+    monkeypatch.setenv("LOLB200_DEFER_QUEUE", "64")
+    b = _render(lb, scene, w, h, options=lb.Options.default(variant=4, defer_cap_primary=8, defer_cap_shadow=4))
+    _same(a, b)
+    # frame after frame on one renderer: the queue re-arms itself
+    r = b["renderer"]
+    frame = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+    for _ in range(3):
+        frame.zero_()
+        r.render_device(frame.data_ptr(), w, h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32), a["rgba"])
+
+
+def test_deferred_rays_on_shards_slabs_and_ragged_frames(scenes_dir):
+    """Shards (compact and full-frame destinations), the slab pipeline of the host-surface path (eight
+    overlapping launch pairs, one queue partition each) and frames that are no multiple of the tile."""
+    import loltracer_b200 as lb
+
+    scene = _scene(lb, "scene3", scenes_dir)
+    opt = lb.Options.default(variant=4, defer_cap_primary=12, defer_cap_shadow=6)
+    r1, r4 = lb.Renderer(scene, lb.Options.default(variant=1)), lb.Renderer(scene, opt)
+    st = torch.cuda.current_stream().cuda_stream
+    for (w, h) in [(333, 129), (1283, 721), (7, 5)]:
+        one = np.zeros((h, w), np.uint32)
+        r1.render_host(one.ctypes.data, w, h)
+        host = np.zeros((h, w), np.uint32)
+        r4.render_host(host.ctypes.data, w, h)
+        assert np.array_equal(host, one), (w, h)
+        for world in (2, 3):
+            frame = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+            for rank in range(world):
+                r4.render_device(frame.data_ptr(), w, h, pitch_px=w, stream=st,
+                                 shard=lb.Shard(rank=rank, world=world, dst_full_frame=1))
+            torch.cuda.synchronize()
+            assert np.array_equal(frame.cpu().numpy().view(np.uint32), one), (w, h, world)
+            shard_px = lb.shard_pixels(w, h, world)
+            gathered = torch.zeros((world, shard_px), dtype=torch.int32, device="cuda:0")
+            for rank in range(world):
+                r4.render_device(gathered[rank].data_ptr(), w, h, pitch_px=w, stream=st,
+                                 shard=lb.Shard(rank=rank, world=world))
+            frame.zero_()
+            lb.deinterleave(gathered.data_ptr(), frame.data_ptr(), w, h, world, shard_px, stream=st)
+            torch.cuda.synchronize()
+            assert np.array_equal(frame.cpu().numpy().view(np.uint32), one), (w, h, world)
+    r1.close()
+    r4.close()

@@ -164,14 +164,16 @@ def test_resumable_pipeline_on_random_scenes_and_edge_cameras(seed, tmp_path):
             _same(ol.cpu_pipeline_render(L, lb, scene, w, h, camera=cam), want)
 
 
-def test_staged_variant_compiles_for_sm_100a(scenes_dir):
-    """Variant 4's device text (the per-pixel function, no kernel yet) goes through NVRTC for sm_100a."""
+def test_deferred_rays_variant_compiles_for_sm_100a(scenes_dir):
+    """Variant 4's program -- lol_render with caps and the continuation queue, lol_resume -- goes through
+    NVRTC for sm_100a, and its march loops are no longer than variant 1's (the cap costs one compare)."""
     import loltracer_b200 as lb
 
     scene = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
     opt = lb.Options.default(variant=4)
     image = lb.compile_cubin(lb.lower_cuda(scene, opt), opt)
-    assert len(image) > 1000
+    sass = lb.disassemble(image)
+    assert "lol_render" in sass and "lol_resume" in sass
 
 
 @pytest.mark.parametrize("seed", range(6))
