@@ -223,6 +223,19 @@ typedef struct lolb200_options {
 	                            divisions in seven it saves), so off by default    */
 	int32_t defer_cap_primary;  /* variant 4: evaluations of a primary / shadow march  */
 	int32_t defer_cap_shadow;   /* before the pixel is put aside; 0 = default (48, 24) */
+	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
+	                            materials of a composite's children,
+	                            naive_renderer.c:102-112): 1 = a hit on a composite
+	                            object takes the material of the child that decides
+	                            the node's distance at the hit point -- the nearer
+	                            child of a (smooth) union, the farther of an
+	                            intersection, a or the carved-out b of a difference,
+	                            ties keep a -- evaluated once per hit pixel at
+	                            p = ro + rd * dist with the IEEE forms.  A node whose
+	                            material is #0 (the field's default) inherits its
+	                            parent's.  Distances, ids and the hit mask do not
+	                            change.  Checked against the oracle's own restatement
+	                            only (oracle/lol_oracle.c: child_material)          */
 } lolb200_options;
 void lolb200_options_default(lolb200_options* o);
 

@@ -91,9 +91,10 @@ struct lolb200_renderer {
 	int threads = LOLB200_KERNEL_THREADS; /* CTA size the program was generated for */
 	size_t dyn_smem = 0; /* variant 2: warp-private queues */
 	cudaKernel_t resume_kernel = nullptr; /* variant 4: lol_resume */
-	lol_u32* queue = nullptr;     /* variant 4: continuation records of all slots, SoA per slot partition */
-	size_t queue_slots = 0;       /* per work-counter slot */
-	lol_u32* queue_ctl = nullptr; /* per slot: [0] pushed, [1] next to resume, [2] finished CTAs (+ pad) */
+	lol_u32* queue[LOL_MAX_SLABS] = {};    /* variant 4: continuation queues of each work-counter slot */
+	size_t queue_slots[LOL_MAX_SLABS] = {}; /* records per queue (one queue per class: 1 + lights) */
+	int queue_classes = 0;
+	lol_u32* queue_ctl = nullptr; /* per slot 64 words: per class (pushed, next to resume), then finished CTAs */
 	lol_u32* counter = nullptr; /* device: [0] next chunk, [1] finished CTAs */
 	lol_u64* stats = nullptr;   /* device: 8 accumulators (options.counters) */
 	/* render_host staging */
@@ -459,7 +460,8 @@ extern "C" void lolb200_renderer_destroy(lolb200_renderer* r) {
 			if (st)
 				cudaStreamDestroy(st);
 		cudaFree(r->frame);
-		cudaFree(r->queue);
+		for (lol_u32* q : r->queue)
+			cudaFree(q);
 		cudaFree(r->queue_ctl);
 		cudaFree(r->counter);
 		cudaFree(r->stats);
@@ -547,8 +549,9 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 	CREATE_TRY(cudaLibraryGetKernel(&r->kernel, r->lib, "lol_render"));
 	if (strstr(r->source.c_str(), "#define LOL_VARIANT 4")) {
 		CREATE_TRY(cudaLibraryGetKernel(&r->resume_kernel, r->lib, "lol_resume"));
-		CREATE_TRY(cudaMalloc(&r->queue_ctl, 4 * LOL_MAX_SLABS * sizeof(lol_u32)));
-		CREATE_TRY(cudaMemset(r->queue_ctl, 0, 4 * LOL_MAX_SLABS * sizeof(lol_u32)));
+		r->queue_classes = 1 + (int)s->n_lights;
+		CREATE_TRY(cudaMalloc(&r->queue_ctl, 64 * LOL_MAX_SLABS * sizeof(lol_u32)));
+		CREATE_TRY(cudaMemset(r->queue_ctl, 0, 64 * LOL_MAX_SLABS * sizeof(lol_u32)));
 	}
 	{
 		/* the lowering states what it generated */
@@ -824,25 +827,25 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 		grid = grid_needed;
 	if (r->resume_kernel) {
 		/* Variant 4: room for a quarter of the launch's pixels in the continuation queue (17 words per
-		 * record); when it overflows, lanes finish their pixels in place.  One partition per
-		 * work-counter slot, so slab launches do not share a queue. */
+		 * record, one queue per class); when it overflows, lanes finish their pixels in place.
+		 * Every work-counter slot has its own queues, so slab launches do not share any. */
 		const size_t px = (size_t)P.n_chunks * P.chunk_w * LOL_BAND_ROWS;
 		size_t want = px / 4 < 65536 ? 65536 : px / 4;
 		if (const char* e = getenv("LOLB200_DEFER_QUEUE")) /* tests: a tiny queue exercises the overflow path */
 			if (atol(e) > 0)
 				want = (size_t)atol(e);
 		want = (want + 31) & ~(size_t)31;
-		if (r->queue_slots < want) {
+		if (r->queue_slots[counter_slot] < want) {
 			CUDA_TRY(cudaDeviceSynchronize()); /* no launch may still use the old queue */
-			cudaFree(r->queue);
-			r->queue = nullptr;
-			r->queue_slots = 0;
-			CUDA_TRY(cudaMalloc(&r->queue, want * 17 * sizeof(lol_u32) * LOL_MAX_SLABS));
-			r->queue_slots = want;
+			cudaFree(r->queue[counter_slot]);
+			r->queue[counter_slot] = nullptr;
+			r->queue_slots[counter_slot] = 0;
+			CUDA_TRY(cudaMalloc(&r->queue[counter_slot], want * 16 * sizeof(lol_u32) * r->queue_classes));
+			r->queue_slots[counter_slot] = want;
 		}
-		P.q = r->queue + (size_t)counter_slot * r->queue_slots * 17;
-		P.q_cap = (lol_u32)r->queue_slots;
-		P.q_ctl = r->queue_ctl + 4 * counter_slot;
+		P.q = r->queue[counter_slot];
+		P.q_cap = (lol_u32)r->queue_slots[counter_slot];
+		P.q_ctl = r->queue_ctl + 64 * counter_slot;
 		P.cap_primary = r->opt.defer_cap_primary > 0 ? (lol_u32)r->opt.defer_cap_primary : 48u;
 		P.cap_shadow = r->opt.defer_cap_shadow > 0 ? (lol_u32)r->opt.defer_cap_shadow : 24u;
 	}

@@ -1725,6 +1725,97 @@ static int has_table_loop(const lolb200_scene* s, int threshold) {
 	return found;
 }
 
+/* ---------------------------------------------- per-child materials (extension) */
+
+/* material of a node with #0 meaning "my parent's" */
+static uint32_t effective_material(const lolb200_object* o, uint32_t inherited) {
+	return o->material ? o->material : inherited;
+}
+
+/* does any leaf below idx end up with a material other than `m`? */
+static int subtree_has_other_material(const lolb200_scene* s, uint32_t idx, uint32_t inherited, uint32_t m) {
+	const lolb200_object* o = &s->nodes[idx];
+	const uint32_t eff = effective_material(o, inherited);
+	if (!LOLB200_OBJ_HAS_CHILDREN(o->type))
+		return eff != m;
+	return subtree_has_other_material(s, (uint32_t)o->a, eff, m) ||
+	       subtree_has_other_material(s, (uint32_t)o->b, eff, m);
+}
+
+/* distance t<N> (IEEE forms, the reference's operation order) and material m<N> of a subtree */
+static int emit_mat_node(struct cgen* g, uint32_t idx, uint32_t inherited) {
+	const lolb200_object* o = &g->s->nodes[idx];
+	const uint32_t eff = effective_material(o, inherited);
+	int me;
+	if (!LOLB200_OBJ_HAS_CHILDREN(o->type)) {
+		me = emit_node(g, idx);
+		sb_printf(g->out, "%sconst lol_u32 m%d = %uu;\n", g->indent, me, eff);
+		return me;
+	}
+	const int a = emit_mat_node(g, (uint32_t)o->a, eff);
+	const int b = emit_mat_node(g, (uint32_t)o->b, eff);
+	me = g->tmp++;
+	switch (o->type) {
+	case LOLB200_OBJ_UNION:
+		sb_printf(g->out, "%sconst float t%d = lol_csg_union(t%d, t%d);\n", g->indent, me, a, b);
+		sb_printf(g->out, "%sconst lol_u32 m%d = (t%d < t%d) ? m%d : m%d;\n", g->indent, me, b, a, b, a);
+		break;
+	case LOLB200_OBJ_INTERSECTION:
+		sb_printf(g->out, "%sconst float t%d = lol_csg_inter(t%d, t%d);\n", g->indent, me, a, b);
+		sb_printf(g->out, "%sconst lol_u32 m%d = (t%d > t%d) ? m%d : m%d;\n", g->indent, me, b, a, b, a);
+		break;
+	case LOLB200_OBJ_DIFFERENCE:
+		sb_printf(g->out, "%sconst float t%d = lol_csg_diff(t%d, t%d);\n", g->indent, me, a, b);
+		sb_printf(g->out, "%sconst lol_u32 m%d = (-t%d > t%d) ? m%d : m%d;\n", g->indent, me, b, a, b, a);
+		break;
+	default:
+		sb_printf(g->out, "%sconst float t%d = lol_smin(t%d, t%d, ", g->indent, me, a, b);
+		sb_float(g->out, o->smoothness);
+		sb_printf(g->out, ");\n");
+		sb_printf(g->out, "%sconst lol_u32 m%d = (t%d < t%d) ? m%d : m%d;\n", g->indent, me, b, a, b, a);
+		break;
+	}
+	return me;
+}
+
+/* lol_scene_materials[] (by material index) and lol_child_material(): one case per top-level
+ * object whose leaves do not all share its material; every other id keeps its object's. */
+static void emit_child_materials(struct sb* out, const lolb200_scene* s) {
+	sb_printf(out, "__device__ const lol_u32 lol_scene_materials[] = {\n");
+	for (uint32_t mi = 0; mi < s->n_materials; mi++) {
+		const lolb200_material* m = &s->materials[mi];
+		const float row[10] = {m->shininess,   m->diffuse[0],  m->diffuse[1], m->diffuse[2],
+		                       m->specular[0], m->specular[1], m->specular[2], m->ambient[0],
+		                       m->ambient[1],  m->ambient[2]};
+		sb_printf(out, "\t/* material #%u */ ", mi);
+		for (int k = 0; k < 10; k++) {
+			sb_bits(out, row[k]);
+			sb_printf(out, ", ");
+		}
+		sb_printf(out, "0u, 0u,\n");
+	}
+	sb_printf(out, "};\n__device__ const lol_u32 lol_object_material[] = {0u");
+	for (uint32_t i = 0; i < s->n_objects; i++)
+		sb_printf(out, ", %uu", s->nodes[s->objects[i]].material);
+	sb_printf(out, "};\n"
+	               "// The material at a hit point of object `id` (extension: options.child_materials).\n"
+	               "__device__ __noinline__ lol_u32 lol_child_material(float x, float y, float z, lol_u32 id) {\n"
+	               "\tswitch (id) {\n");
+	for (uint32_t i = 0; i < s->n_objects; i++) {
+		const uint32_t root = s->objects[i];
+		const lolb200_object* o = &s->nodes[root];
+		struct cgen g = {.s = s, .out = out, .indent = "\t\t"};
+		int t;
+		if (!LOLB200_OBJ_HAS_CHILDREN(o->type) || !subtree_has_other_material(s, root, o->material, o->material))
+			continue;
+		sb_printf(out, "\tcase %uu: {\n", i + 1);
+		t = emit_mat_node(&g, root, o->material);
+		sb_printf(out, "\t\treturn m%d;\n\t}\n", t);
+		cgen_release(&g);
+	}
+	sb_printf(out, "\tdefault: return lol_object_material[id];\n\t}\n}\n");
+}
+
 /* ------------------------------------------------------------------- driver */
 
 static void emit_tables(struct sb* out, const lolb200_scene* s) {
@@ -1800,6 +1891,8 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;
 	if (variant == 2 && s->n_objects > 65535u)
 		variant = 1; /* variant 2 keeps object ids in 16 bits */
+	if (variant == 4 && s->n_lights > 30u)
+		variant = 1; /* variant 4: one continuation queue per light, counters packed in bytes */
 	if (variant < 1 || variant > 4) {
 		lolb200_set_error("unknown kernel variant %d", variant);
 		return NULL;
@@ -1867,6 +1960,9 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	sb_putn(&out, lol_params_text, strlen(lol_params_text));
 	sb_putn(&out, lol_kernel_text, (size_t)(marker - lol_kernel_text));
 	emit_tables(&out, s);
+	sb_printf(&out, "#define LOL_CHILD_MATERIALS %d\n", o.child_materials != 0);
+	if (o.child_materials)
+		emit_child_materials(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
 	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */,
 	         o.pack_pairs);

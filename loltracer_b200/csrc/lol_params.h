@@ -41,9 +41,9 @@ struct lol_params {
 	lol_u32 done_value;
 	// variant 4 (deferred long rays): a march that is not over after cap_* evaluations puts its pixel aside
 	lol_u32 cap_primary, cap_shadow;
-	lol_u32 q_cap;        // slots in the continuation queue
-	lol_u32* q;           // records, structure of arrays: word f of slot s at q[f * q_cap + s]
-	lol_u32* q_ctl;       // [0] records pushed, [1] next record to resume, [2] finished CTAs of lol_resume
+	lol_u32 q_cap;        // slots per continuation queue (one queue per class: lol_kernel.cuh)
+	lol_u32* q;           // records of 16 words, queue c at q + c * q_cap * 16
+	lol_u32* q_ctl;       // per class [2c] records pushed, [2c + 1] next to resume; then finished CTAs of lol_resume
 };
 
 #define LOL_BAND_ROWS 4

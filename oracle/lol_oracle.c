@@ -17,6 +17,8 @@
  * mode 2 = the pipeline of mode 0 around a per-scene SPECIALISED distance
  * function handed in by the caller (lolo_set_specialised_sdf): the CPU timing
  * stand-in for the DynASM JIT, which cannot be built here (no Lua).
+ * mode | 0x100 = per-child materials, an extension of ours (child_material below;
+ * parity for it UNPINNED: the reference has no such feature).
  */
 #include <math.h>
 #include <pthread.h>
@@ -145,9 +147,38 @@ static struct world_dist sdf_jit(const lolb200_scene* s, V3 p) {
 	return r;
 }
 
+/* EXTENSION (lolb200_options.child_materials).  The reference ignores the materials of a
+ * composite's children (naive_renderer.c:102-112): this is OUR definition, restated here and in the lowering
+ * (lol_lower.c: emit_mat_node) -- parity for it is against this file only ("unpinned").
+ * The material of a hit on a composite object is the material of the child that decides the node's distance
+ * at the hit point: the nearer child of a (smooth) union, the farther one of an intersection, a -- or b
+ * where b carves -- of a difference; ties keep a.  A node whose material is #0 (the field's default after
+ * scene.c:124's memset) inherits its parent's.  Distances are the naive renderer's (obj_dist). */
+static float child_material(const lolb200_scene* s, const lolb200_object* o, V3 p, uint32_t inherited,
+                            uint32_t* mat) {
+	const uint32_t eff = o->material ? o->material : inherited;
+	uint32_t ma, mb;
+	float a, b;
+	if (!LOLB200_OBJ_HAS_CHILDREN(o->type)) {
+		*mat = eff;
+		return obj_dist(s, o, p);
+	}
+	a = child_material(s, &s->nodes[o->a], p, eff, &ma);
+	b = child_material(s, &s->nodes[o->b], p, eff, &mb);
+	switch (o->type) {
+	case LOLB200_OBJ_UNION: *mat = (b < a) ? mb : ma; return minf_(a, b);
+	case LOLB200_OBJ_INTERSECTION: *mat = (b > a) ? mb : ma; return maxf_(a, b);
+	case LOLB200_OBJ_DIFFERENCE: *mat = (-b > a) ? mb : ma; return maxf_(a, -b);
+	default: *mat = (b < a) ? mb : ma; return sminf_(a, b, o->smoothness);
+	}
+}
+
+#define LOLO_MODE_CHILD_MATERIALS 0x100 /* OR-ed into `mode` */
+
 struct ctx {
 	const lolb200_scene* s;
 	int mode;
+	int child_materials;
 	uint32_t n_primary, n_normal, n_shadow;
 };
 
@@ -224,8 +255,12 @@ static V3 get_normal(struct ctx* c, V3 p, float dist) {
 /* get_light (naive_renderer.c:128-175) with get_material (:102-112) */
 static V3 get_light(struct ctx* c, V3 p, V3 n, uint32_t id) {
 	const lolb200_scene* s = c->s;
-	const lolb200_material* mat =
-		&s->materials[id ? s->nodes[s->objects[id - 1]].material : 0];
+	uint32_t mi = id ? s->nodes[s->objects[id - 1]].material : 0;
+	if (id && c->child_materials) {
+		const lolb200_object* top = &s->nodes[s->objects[id - 1]];
+		child_material(s, top, p, top->material, &mi);
+	}
+	const lolb200_material* mat = &s->materials[mi];
 	V3 total = {0.f, 0.f, 0.f};
 	V3 cam_pos = from3(s->camera.point);
 
@@ -271,7 +306,7 @@ struct job {
  * hoisted (get_camera_ray recomputes the same values per pixel, :178-188). */
 static void* worker(void* arg) {
 	struct job* j = arg;
-	struct ctx c = {.s = j->s, .mode = j->mode};
+	struct ctx c = {.s = j->s, .mode = j->mode & 0xff, .child_materials = (j->mode & LOLO_MODE_CHILD_MATERIALS) != 0};
 	float fwidth = j->w, fheight = j->h;
 	V3 ro = from3(j->cb.origin), dir = from3(j->cb.dir);
 	V3 right = from3(j->cb.right), up = from3(j->cb.up);

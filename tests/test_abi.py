@@ -44,7 +44,7 @@ def test_struct_layouts_match_c(tmp_path):
     pods = {"lolb200_material": (api.Material, "ambient"), "lolb200_light": (api.Light, "specular_intensity"),
             "lolb200_object": (api.Object, "b"), "lolb200_camera": (api.Camera, "fov"),
             "lolb200_scene": (api.SceneStruct, "camera"), "lolb200_camera_basis": (api.CameraBasis, "height"),
-            "lolb200_options": (api.Options, "defer_cap_shadow"), "lolb200_pixfmt": (api.PixFmt, "amask"),
+            "lolb200_options": (api.Options, "child_materials"), "lolb200_pixfmt": (api.PixFmt, "amask"),
             "lolb200_shard": (api.Shard, "done_value"), "lolb200_aux": (api.Aux, "launch_timing")}
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lolb200.h"\nint main(void) {\n' + "".join(
@@ -58,7 +58,7 @@ def test_struct_layouts_match_c(tmp_path):
         seen[name] = (int(size), int(off))
     for name, (cls, last) in pods.items():
         assert seen[name] == (C.sizeof(cls), getattr(cls, last).offset), name
-    assert C.sizeof(api.Options) == 72 and C.sizeof(api.Shard) == 32
+    assert C.sizeof(api.Options) == 76 and C.sizeof(api.Shard) == 32
 
 
 def test_no_cpu_fallback(scenes_dir):

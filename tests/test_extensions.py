@@ -134,3 +134,85 @@ def test_gpu_renders_csg_scenes_like_the_oracle(variant):
         got = _render(lb, scene, w, h, options=lb.Options.default(variant=variant, guarded_fastpath=2))
         _check(got, ol.port_render(scene, w, h))
         got["renderer"].close()
+
+
+# ---- per-child materials (lolb200_options.child_materials) -------------------------------
+
+CHILD_MATERIALS_SCENE = """materials {
+  { shininess = 0, diffuse = (0,0,0), specular = (0,0,0), ambient = (0,0,0) },
+  { shininess = 8, diffuse = (0.8,0.1,0.1), specular = (0.3,0.3,0.3), ambient = (0.8,0.1,0.1) },
+  { shininess = 30, diffuse = (0.1,0.8,0.1), specular = (0.5,0.5,0.5), ambient = (0.1,0.8,0.1) },
+  { shininess = 2, diffuse = (0.1,0.1,0.9), specular = (0.1,0.1,0.1), ambient = (0.1,0.1,0.9) },
+  { shininess = 4, diffuse = (0.6,0.6,0.2), specular = (0.2,0.2,0.2), ambient = (0.6,0.6,0.2) } }
+scene { ambient { color = (0.2, 0.2, 0.2) },
+  camera { point = (0, 2, 5), direction = (0, -0.2, -1), fov = 90 },
+  point_light { point = (4, 8, 3), diffuse_intensity = (1,1,1), specular_intensity = (1,1,1) },
+  point_light { point = (-6, 3, 0), diffuse_intensity = (0.5,0.5,0.8), specular_intensity = (0.5,0.5,0.8) },
+  smooth_union { material = #1, smoothness = 0.8,
+    a = sphere { material = #2, point = (-1.2, 1, -5), radius = 1.2 },
+    b = smooth_union { smoothness = 0.5,
+          a = sphere { material = #3, point = (1.0, 1.2, -5.5), radius = 1.0 },
+          b = box { point = (0, 2.6, -5), point2 = (0.6, 0.3, 0.6), radius = 0.1 } } },
+  %s
+  plane { material = #4, y = -0.5 } }"""
+CSG_PART = """difference { material = #2,
+    a = intersection { a = sphere { material = #3, point = (3.5, 1, -6), radius = 1.4 },
+                       b = box { material = #1, point = (3.5, 1, -6), point2 = (1.1, 1.1, 1.1), radius = 0 } },
+    b = sphere { material = #4, point = (3.5, 1.6, -4.9), radius = 0.8 } },"""
+
+
+@pytest.mark.parametrize("csg", [False, True])
+def test_child_materials_on_the_cpu_pipeline(csg, tmp_path):
+    """The generated program with options.child_materials (lol_child_material: the winning top-level object's
+    tree once more at the hit point, IEEE forms, with a material select per node) compiled for the host against
+    the oracle's restatement (mode | 0x100): every pixel, RGB exact.  The unset material of the inner smooth
+    union and of the box inherit their parent's; distances, ids and step counts do not depend on the option;
+    with the option off the frame is the reference's (children ignored)."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_string(CHILD_MATERIALS_SCENE % (CSG_PART if csg else ""))
+    w, h = 96, 54
+    frames = {}
+    for on in (0, 1):
+        src = lb.lower_cuda(scene, lb.Options.default(variant=1, child_materials=on))
+        assert f"#define LOL_CHILD_MATERIALS {on}" in src
+        L = ol.cpu_pipeline(tmp_path, src, f"cm{int(csg)}{on}")
+        got = ol.cpu_pipeline_render(L, lb, scene, w, h)
+        want = ol.port_render(scene, w, h, mode=0x100 if on else 0, counts=True)
+        for k in ("rgba", "id", "nprimary"):
+            assert np.array_equal(got[k], want[k]), (on, k)
+        assert np.array_equal(got["dist"].view(np.uint32), want["dist"].view(np.uint32))
+        frames[on] = got
+    assert np.array_equal(frames[0]["id"], frames[1]["id"])
+    assert np.array_equal(frames[0]["dist"].view(np.uint32), frames[1]["dist"].view(np.uint32))
+    blob = frames[0]["id"] == 1
+    differs = frames[0]["rgba"] != frames[1]["rgba"]
+    assert differs[blob].mean() > 0.5          # the blob's children show their own colours
+    assert not differs[~(blob | (frames[0]["id"] == 2) & csg)].any()   # nothing else changes
+    if not ol.have_ref():
+        return
+    # option off == the reference itself (children's materials ignored); the extension nodes are not its
+    if not csg:
+        ref = ol.RefScene(text=CHILD_MATERIALS_SCENE % "").probe(w, h)
+        assert np.array_equal(frames[0]["rgba"], ref["rgba"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+def test_child_materials_on_the_gpu(variant):
+    """Every kernel variant with options.child_materials against the oracle's restatement at 1280x720."""
+    import torch
+
+    import loltracer_b200 as lb
+    from test_gpu_parity import _check, _render
+
+    scene = lb.Scene.from_string(CHILD_MATERIALS_SCENE % CSG_PART)
+    w, h = 1280, 720
+    want = ol.port_render(scene, w, h, mode=0x100)
+    got = _render(lb, scene, w, h, options=lb.Options.default(variant=variant, child_materials=1))
+    _check(got, want)
+    plain = _render(lb, scene, w, h, options=lb.Options.default(variant=variant))
+    _check(plain, ol.port_render(scene, w, h))
+    assert (plain["rgba"] != got["rgba"]).mean() > 0.05
+    got["renderer"].close()
+    plain["renderer"].close()

@@ -16,7 +16,9 @@ if name.startswith("synthetic"):
 else:
     scene = lb.Scene.from_file(os.path.join(ROOT, "tests", "golden", "scenes", name + ".lol"))
 extra = dict(kv.split("=") for kv in os.environ.get("LOL_OPTS", "").split(",") if kv)
-r = lb.Renderer(scene, lb.Options.default(variant=variant, arith=arith, **{k: int(v) for k, v in extra.items()}))
+kw = dict(variant=variant, arith=arith)
+kw.update({k: int(v) for k, v in extra.items()})  # LOL_OPTS may override the positional variant
+r = lb.Renderer(scene, lb.Options.default(**kw))
 frame = torch.zeros((h, w), dtype=torch.int32, device="cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 st = torch.cuda.current_stream().cuda_stream
