@@ -223,6 +223,10 @@ typedef struct lolb200_options {
 	                            divisions in seven it saves), so off by default    */
 	int32_t defer_cap_primary;  /* variant 4: evaluations of a primary / shadow march  */
 	int32_t defer_cap_shadow;   /* before the pixel is put aside; 0 = default (48, 24) */
+	int32_t roll_v1;            /* variants 1 and 4, instruction-cache footprint: 1 = the four
+	                            normal taps are a loop around ONE copy of the distance
+	                            code, 2 = the lights as well; 0 = everything unrolled;
+	                            -1 = default                                        */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

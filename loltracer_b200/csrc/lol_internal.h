@@ -21,6 +21,8 @@ int lolb200_div_const_is_exact(float k);
 #define LOLB200_KERNEL_THREADS 256
 /* Kernel structure used when options.variant == 0 (1 phase-sequential, 2 compaction). */
 #define LOLB200_DEFAULT_VARIANT 1
+/* options.roll_v1 = -1: what variants 1 and 4 roll into loops by default (0 nothing, 1 normal taps, 2 + lights) */
+#define LOLB200_DEFAULT_ROLL_V1 0
 
 #ifdef __cplusplus
 }

@@ -1942,6 +1942,8 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		else
 			sb_printf(&out, "#define LOL_LAUNCH_BOUNDS __launch_bounds__(%d)\n", threads);
 		sb_printf(&out, "#define LOL_ROLL_PHASES %d\n", o.roll_phases != 0);
+		/* default: unrolled until measured otherwise */
+		sb_printf(&out, "#define LOL_ROLL_V1 %d\n", o.roll_v1 < 0 ? LOLB200_DEFAULT_ROLL_V1 : o.roll_v1);
 	}
 	if (variant == 2) {
 		/* struct lol_warp_smem (lol_kernel.cuh): p, n, t|px, dir, sh[lights], id,
