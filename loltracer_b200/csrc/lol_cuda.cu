@@ -668,6 +668,25 @@ static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands
 	return min_w;
 }
 
+/* How many CTAs per SM a launch uses.  A frame's time is bounded below by its slowest warp: a tile
+ * with a floor-grazing ray marches ~500 distance evaluations one after the other, and with 8 warps per
+ * scheduler every warp gets an eighth of the issue slots.  A whole 4K frame has 55 tiles per warp and
+ * hides that; one rank's shard of eight has 7, and the slowest tile (started first: longest-first
+ * order) then runs as long as the whole launch (measured: 76 us of tail in a 337 us launch).  With
+ * fewer resident warps each one issues more often, so small launches trade a little throughput for
+ * a shorter critical path.  LOLB200_CTAS_PER_SM=<n> forces a value (A/B). */
+static int resident_ctas_per_sm(const lolb200_renderer* r, lol_u32 n_chunks) {
+	static const int forced = [] {
+		const char* e = getenv("LOLB200_CTAS_PER_SM");
+		return e ? atoi(e) : 0;
+	}();
+	int ctas = r->blocks_per_sm;
+	if (forced > 0)
+		return forced < ctas ? forced : ctas;
+	(void)n_chunks;
+	return ctas;
+}
+
 __global__ void lol_iota_kernel(lol_u32* v, lol_u32 n) {
 	const lol_u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n)
@@ -821,7 +840,7 @@ static int launch_bands(lolb200_renderer* r, const lolb200_camera* cam, int w, i
 		P.order = r->lpt.have_order ? r->lpt.order : nullptr;
 	}
 	const size_t warps_needed = P.n_chunks;
-	size_t grid = (size_t)r->sm_count * r->blocks_per_sm;
+	size_t grid = (size_t)r->sm_count * resident_ctas_per_sm(r, P.n_chunks);
 	const size_t grid_needed = (warps_needed + r->threads / 32 - 1) / (r->threads / 32);
 	if (grid > grid_needed)
 		grid = grid_needed;

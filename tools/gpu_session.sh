@@ -17,6 +17,7 @@
 #   multi_tests       the multi-GPU tests (tests/test_gpu_backend.py, tests/test_gpu_sharding.py)
 #   headless[:<Ns>]   the renderer.h drop-in (headless main.c twin) with --gpus N, host and peer gathers
 #   py:<name>:<script+args>                  any python script under tools/
+#   sh:<name>:<command with + for spaces>    any shell command (environment variables in front of a tool)
 tag=${1:-session}
 shift
 out=gpurun_out/$tag
@@ -96,6 +97,8 @@ for stage in "$@"; do
       done ;;
     py)
       timeout 900 python tools/${b//+/ } > $out/$a.txt 2>&1; echo "$a rc=$?"; tail -40 $out/$a.txt ;;
+    sh) # sh:<name>:<shell command with + for spaces> (e.g. an environment variable in front of a tool)
+      timeout 900 bash -c "${b//+/ }" > $out/$a.txt 2>&1; echo "$a rc=$?"; tail -40 $out/$a.txt ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
