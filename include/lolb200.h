@@ -227,6 +227,11 @@ typedef struct lolb200_options {
 	                            normal taps are a loop around ONE copy of the distance
 	                            code, 2 = the lights as well; 0 = everything unrolled;
 	                            -1 = default                                        */
+	int32_t loop_worklist;      /* pruned table loops: 1 = every lane collects the rows it
+	                            cannot skip and the warp drains the lists together, each
+	                            lane its own row per round (rounds = the longest list,
+	                            not the union of all lanes' rows); 0 = the plain loops;
+	                            -1 = default (1).  Exact either way                  */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

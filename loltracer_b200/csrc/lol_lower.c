@@ -742,6 +742,8 @@ static void bound_row(const lolb200_scene* s, uint32_t idx, float row[LOL_BOUND_
 /* objects per group; options.prune_group, set by lolb200_lower_cuda for the calling thread */
 static _Thread_local uint32_t lol_group = 8;
 #define LOL_GROUP lol_group
+/* pruned table loops as per-lane work lists (emit_sdf_fn; options.loop_worklist) */
+static _Thread_local int lol_worklist = 1;
 
 struct morton_key {
 	uint32_t key, idx;
@@ -1286,6 +1288,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				 * Any order is legal: ties are broken by object id, the reference's
 				 * "first of equal distances" (naive_renderer.c:39). */
 				const int use_hint = !packed_ret;
+				/* Work lists (single ray, the program's main form): see the comment at the
+				 * generated code below.  128 rows per block, LOL_GROUP must divide it. */
+				const int worklist = lol_worklist && !two && !packed_ret && 128u % LOL_GROUP == 0u;
 				float(*boxes)[LOL_BOUND_SLOTS] = malloc(sizeof *boxes * n);
 				uint32_t* order = malloc(sizeof *order * n);
 				uint32_t* rowof = malloc(sizeof *rowof * n);
@@ -1318,9 +1323,110 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					struct cgen r = {.s = s, .out = (q == 0) ? &body : &scratch, .in_loop = 1,
 					                 .indent = "\t\t\t", .fast = fast, .div_ok = div_ok, .two = two, .pack = pack, .pc = &pc,
 		                 .lay_pack = lay_pack, .lay_div_ok = lay_div_ok};
-					const char* best_args = two ? "bestA, bestB" : "best";
-					const char* sfx = two ? "2" : "";
+				const char* best_args = two ? "bestA, bestB" : "best";
+				const char* sfx = two ? "2" : "";
+				if (worklist) {
+					/* Per-lane work lists.  The plain loops below walk groups and members with a
+					 * warp-uniform index: every lane tests, and the warp then evaluates the UNION of
+					 * what its lanes could not skip (21 of 32 lanes per instruction on the
+					 * 1024-sphere scene).  Here every lane first COLLECTS the rows it cannot skip as
+					 * bits (group tests, member tests: cheap, uniform), then the warp drains the lists
+					 * together: in each round every lane evaluates ITS next row -- different rows in
+					 * one instruction stream, read from shared memory with per-lane addresses -- so
+					 * the rounds number the longest list, not the union.  Any order is legal (ties go
+					 * to the smaller object id); a row is re-tested against the current `best` when
+					 * it is popped, because earlier rows may have tightened it. */
+					const uint32_t nblk = (n + 127u) / 128u, gpb = 128u / LOL_GROUP;
+					const unsigned cost = node_cost(s, s->objects[i]) + 1u;
+					struct sb* const real_out = r.out;
+					struct sb sink = {0};
 					if (q == 0) {
+						sb_printf(&body, "\t{\n");
+						if (use_hint)
+							sb_printf(&body,
+							          "\tconst int hrow = (hint >= %uu && hint < %uu) ? (int)lol_run%d_rowof[hint - %uu] : -1;\n",
+							          i + 1, j + 1, run_no, i + 1);
+						else
+							sb_printf(&body, "\tconst int hrow = -1;\n");
+						sb_printf(&body,
+						          "\tlol_u32 m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u; // the rows of the current block this lane cannot skip\n"
+						          "\tint blk = -1, i = hrow;\n"
+						          "\tbool found = hrow >= 0; // the ray's last winner first: it sets a tight `best`\n"
+						          "\tfor (;;) {\n"
+						          "\t\twhile (!found) { // this lane's next row: cheap, per lane\n"
+						          "\t\t\tif ((m0 | m1 | m2 | m3) == 0u) {\n"
+						          "\t\t\t\tif (++blk >= %d)\n\t\t\t\t\tbreak;\n"
+						          "#pragma unroll 1\n"
+						          "\t\t\t\tfor (int g = 0; g < %u; ++g) { // collect: group tests, then member tests\n"
+						          "\t\t\t\t\tconst int gi = blk * %u + g;\n"
+						          "\t\t\t\t\tif (gi >= %u)\n\t\t\t\t\t\tbreak;\n"
+						          "\t\t\t\t\tconst lol_u32* gc = lol_run%d_groups + gi * %d;\n"
+						          "\t\t\t\t\tconst int rows = (gi + 1) * %u <= %u ? %u : %u - gi * %u;\n"
+						          "\t\t\t\t\tif (lol_box_skips(x, y, z, LOL_TF(gc[0]), LOL_TF(gc[1]), LOL_TF(gc[2]), LOL_TF(gc[3]), "
+						          "LOL_TF(gc[4]), LOL_TF(gc[5]), LOL_TF(gc[6]), best)) {\n"
+						          "\t\t\t\t\t\tlol_count_skip((lol_u32)(rows - (hrow >= gi * %u && hrow < gi * %u + rows)) * %uu);\n"
+						          "\t\t\t\t\t\tcontinue;\n\t\t\t\t\t}\n"
+						          "\t\t\t\t\tlol_u32 bits = 0u;\n"
+						          "#pragma unroll 1\n"
+						          "\t\t\t\t\tfor (int k = 0; k < rows; ++k) {\n"
+						          "\t\t\t\t\t\tconst lol_u32* ct = lol_run%d + (gi * %u + k) * LOL_RUN%d_STRIDE;\n"
+						          "\t\t\t\t\t\tif (gi * %u + k == hrow)\n\t\t\t\t\t\t\tcontinue;\n"
+						          "\t\t\t\t\t\tif (lol_box_skips(x, y, z, LOL_TF(ct[0]), LOL_TF(ct[1]), LOL_TF(ct[2]), LOL_TF(ct[3]), "
+						          "LOL_TF(ct[4]), LOL_TF(ct[5]), LOL_TF(ct[6]), best))\n"
+						          "\t\t\t\t\t\t\tlol_count_skip(%uu);\n"
+						          "\t\t\t\t\t\telse\n\t\t\t\t\t\t\tbits |= 1u << k;\n"
+						          "\t\t\t\t\t}\n"
+						          "\t\t\t\t\tconst int pos = g * %u;\n"
+						          "\t\t\t\t\tif (pos < 32) m0 |= bits << pos;\n"
+						          "\t\t\t\t\telse if (pos < 64) m1 |= bits << (pos - 32);\n"
+						          "\t\t\t\t\telse if (pos < 96) m2 |= bits << (pos - 64);\n"
+						          "\t\t\t\t\telse m3 |= bits << (pos - 96);\n"
+						          "\t\t\t\t}\n"
+						          "\t\t\t\tcontinue;\n"
+						          "\t\t\t}\n"
+						          "\t\t\tif (m0) { i = __ffs((int)m0) - 1; m0 &= m0 - 1u; }\n"
+						          "\t\t\telse if (m1) { i = 31 + __ffs((int)m1); m1 &= m1 - 1u; }\n"
+						          "\t\t\telse if (m2) { i = 63 + __ffs((int)m2); m2 &= m2 - 1u; }\n"
+						          "\t\t\telse { i = 95 + __ffs((int)m3); m3 &= m3 - 1u; }\n"
+						          "\t\t\ti += blk * 128;\n"
+						          "\t\t\tconst lol_u32* ct = lol_run%d + i * LOL_RUN%d_STRIDE;\n"
+						          "\t\t\t// `best` may be tighter than when the row was collected\n"
+						          "\t\t\tif (lol_box_skips(x, y, z, LOL_TF(ct[0]), LOL_TF(ct[1]), LOL_TF(ct[2]), LOL_TF(ct[3]), "
+						          "LOL_TF(ct[4]), LOL_TF(ct[5]), LOL_TF(ct[6]), best))\n"
+						          "\t\t\t\tlol_count_skip(%uu);\n"
+						          "\t\t\telse\n\t\t\t\tfound = true;\n"
+						          "\t\t}\n"
+						          "\t\tif (!found)\n\t\t\tbreak;\n"
+						          "\t\tfound = false;\n"
+						          "\t\t{ // one round: every lane that has a row evaluates it\n"
+						          "\t\t\tconst lol_u32* c = lol_run%d + i * LOL_RUN%d_STRIDE;\n",
+						          (int)nblk, gpb, gpb, ngroups, run_no, LOL_BOUND_SLOTS,
+						          LOL_GROUP, n, LOL_GROUP, n, LOL_GROUP,
+						          LOL_GROUP, LOL_GROUP, cost,
+						          run_no, LOL_GROUP, run_no, LOL_GROUP, cost, LOL_GROUP,
+						          run_no, run_no, cost, run_no, run_no);
+					}
+					/* row = box (C, H, M), object id, then the object's own constants */
+					r.out = &sink;
+					for (int b = 0; b < LOL_BOUND_SLOTS; b++)
+						cst(&r, boxes[order[q]][b]);
+					cst_raw(&r, k + 1);
+					r.out = real_out;
+					free(sink.p);
+					if (q == 0)
+						sb_printf(&body, "\t\t\tconst lol_u32 oid = c[%d];\n", LOL_BOUND_SLOTS);
+					int t = emit_object(&r, s->objects[k]);
+					if (q == 0)
+						sb_printf(&body,
+						          "\t\t\tif (t%d < best || (t%d == best && oid < bid)) {\n"
+						          "\t\t\t\tbest = t%d;\n\t\t\t\tbid = oid;\n\t\t\t}\n\t\t}\n\t}\n\t}\n",
+						          t, t, t);
+					/* a stride of 4 x odd words: rows read with per-lane addresses fall into different
+					 * 16-byte bank groups unless their numbers agree modulo 8 (Morton neighbours do not) */
+					while ((r.nrow / 4) % 2 == 0)
+						row_push(&r, 0.f);
+				} else {
+				if (q == 0) {
 						sb_printf(&body, "\t{\n");
 						if (use_hint && two)
 							sb_printf(&body,
@@ -1395,6 +1501,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\t\tif (t%d < best || (t%d == best && oid < bid)) {\n"
 						          "\t\t\t\tbest = t%d;\n\t\t\t\tbid = oid;\n\t\t\t}\n\t\t}\n\t}\n\t}\n",
 						          t, t, t);
+				}
 					if (q == 0)
 						per_row = r.nrow;
 					sb_printf(&tables.words, "\n\t");
@@ -1886,6 +1993,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		lolb200_options_default(&o);
 	threshold = o.loop_threshold > 0 ? o.loop_threshold : 16;
 	lol_group = o.prune_group > 0 ? (uint32_t)o.prune_group : 8u;
+	lol_worklist = o.loop_worklist < 0 ? 1 : o.loop_worklist;
 	variant = o.variant;
 	if (variant == 0) /* chosen per scene */
 		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;

@@ -101,6 +101,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->pack_pairs = 1;
 	o->share_first_step = 1;
 	o->roll_v1 = -1;
+	o->loop_worklist = -1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

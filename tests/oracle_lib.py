@@ -206,6 +206,7 @@ static inline float lol_sqrt_fast(float x) { return std::sqrt(x); }
 static inline float lol_fma(float a, float b, float c) { return std::fma(a, b, c); }
 #define __fmaf_rn lol_fma
 static inline int __float2int_rz(float f) { return (int)f; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 """
 
 
