@@ -231,7 +231,8 @@ typedef struct lolb200_options {
 	                            cannot skip and the warp drains the lists together, each
 	                            lane its own row per round (rounds = the longest list,
 	                            not the union of all lanes' rows); 0 = the plain loops;
-	                            -1 = default (1).  Exact either way                  */
+	                            -1 = default (0: measured 11 % slower on B200, the box
+	                            tests dominate, not the rows).  Exact either way     */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

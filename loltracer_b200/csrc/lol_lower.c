@@ -743,7 +743,7 @@ static void bound_row(const lolb200_scene* s, uint32_t idx, float row[LOL_BOUND_
 static _Thread_local uint32_t lol_group = 8;
 #define LOL_GROUP lol_group
 /* pruned table loops as per-lane work lists (emit_sdf_fn; options.loop_worklist) */
-static _Thread_local int lol_worklist = 1;
+static _Thread_local int lol_worklist = 0;
 
 struct morton_key {
 	uint32_t key, idx;
@@ -1993,7 +1993,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		lolb200_options_default(&o);
 	threshold = o.loop_threshold > 0 ? o.loop_threshold : 16;
 	lol_group = o.prune_group > 0 ? (uint32_t)o.prune_group : 8u;
-	lol_worklist = o.loop_worklist < 0 ? 1 : o.loop_worklist;
+	lol_worklist = o.loop_worklist < 0 ? 0 : o.loop_worklist; /* measured slower on B200: off */
 	variant = o.variant;
 	if (variant == 0) /* chosen per scene */
 		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;
