@@ -233,6 +233,12 @@ typedef struct lolb200_options {
 	                            not the union of all lanes' rows); 0 = the plain loops;
 	                            -1 = default (0: measured 11 % slower on B200, the box
 	                            tests dominate, not the rows).  Exact either way     */
+	int32_t near_cache;         /* variant 1, scenes with one pruned table loop: a ray remembers
+	                            the (up to four) rows it could not skip and how far it may
+	                            move before the others must be looked at again, so most
+	                            march steps evaluate the candidates and walk no group box
+	                            at all (lol_kernel.cuh: struct lol_near; exact).
+	                            1 = on, 0 = off, -1 = default (on)                   */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

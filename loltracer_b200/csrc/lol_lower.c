@@ -744,6 +744,13 @@ static _Thread_local uint32_t lol_group = 8;
 #define LOL_GROUP lol_group
 /* pruned table loops as per-lane work lists (emit_sdf_fn; options.loop_worklist) */
 static _Thread_local int lol_worklist = 0;
+/* emit_sdf_fn writes lol_sdf_nr: the pruned loop with the per-ray candidate memory (lol_kernel.cuh: struct lol_near) */
+static _Thread_local int lol_emit_near = 0;
+/* Rows that are read with per-lane addresses (work lists, candidate memory) get a stride of 4 x odd
+ * words: two rows then fall into different 16-byte bank groups of shared memory unless their numbers
+ * agree modulo 8 (Morton neighbours do not).  Every form of a program reads ONE table, so this is
+ * decided per program, not per function. */
+static _Thread_local int lol_pad_rows = 0;
 
 struct morton_key {
 	uint32_t key, idx;
@@ -1076,7 +1083,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 
 	/* The out-of-line fallback hands (distance, id) back in one 64-bit register
 	 * pair; a reference parameter would force the caller's id onto the stack. */
-	const int packed_ret = strcmp(name, "lol_sdf") != 0 && !two; /* (distance, id) in one 64-bit value */
+	const int packed_ret = strcmp(name, "lol_sdf") != 0 && strcmp(name, "lol_sdf_nr") != 0 && !two; /* (distance, id) in one 64-bit value */
 	sb_printf(&body,
 	          "// sdf (naive_renderer.c:30-44): running strict-< minimum over the top-level\n"
 	          "// objects, ids 1..n in file order, (INF, 0) when nothing is closer.\n");
@@ -1094,6 +1101,14 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          attrs, name);
 	else if (packed_ret)
 		sb_printf(&body, "__device__ %s lol_u64 %s(const float x, const float y, const float z) {\n",
+		          attrs, name);
+	else if (lol_emit_near)
+		sb_printf(&body,
+		          "// nr: what the ray remembers of the pruned table loop (struct lol_near); move: an upper bound of\n"
+		          "// the distance between this point and the one of the ray's previous call.  Neither changes the result.\n"
+		          "__device__ %s float %s(const float x, const float y, const float z,\n"
+		          "                                         lol_near& nr, const float move, lol_u32& id) {\n"
+		          "\tconst lol_u32 hint = 0u;\n",
 		          attrs, name);
 	else
 		sb_printf(&body,
@@ -1325,7 +1340,107 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		                 .lay_pack = lay_pack, .lay_div_ok = lay_div_ok};
 				const char* best_args = two ? "bestA, bestB" : "best";
 				const char* sfx = two ? "2" : "";
-				if (worklist) {
+				if (lol_emit_near && !two && !packed_ret) {
+					/* The per-ray candidate memory (lol_kernel.cuh: struct lol_near).  Round 0 evaluates the
+					 * remembered candidates (the last winner first); if the room the ray had is used up,
+					 * every row is looked at again -- tests only -- which gives the rows that cannot be
+					 * skipped now (the new candidates) and the distance to the nearest skipped one (the new
+					 * room); round 1 evaluates the new candidates that round 0 did not.  ONE copy of the
+					 * object's code serves both rounds. */
+					const unsigned cost = node_cost(s, s->objects[i]) + 1u;
+					struct sb* const real_out = r.out;
+					struct sb sink = {0};
+					if (q == 0) {
+						sb_printf(&body,
+						          "\t{\n"
+						          "\tnr.room -= lol_fma(move, LOL_F(0x3f800347 /*1.0001*/), LOL_NEAR_PAD);\n"
+						          "\tconst bool near_ok = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= LOL_NEAR_COORD;\n"
+						          "\tconst lol_u32 list0 = nr.cand;\n"
+						          "\tlol_u32 list = list0;  // rows to evaluate in this round\n"
+						          "\tlol_u32 wrow = 0xffu;  // the row that holds `best`, if a row does\n"
+						          "\tlol_u32 nev = 0u;\n"
+						          "\tbool retest = false; // round 0: the last winner is evaluated untested, the others re-tested\n"
+						          "\tbool slow = false;\n"
+						          "\tfor (int round = 0;; ++round) {\n"
+						          "#pragma unroll 1\n"
+						          "\t\tfor (int k = 0; k < 4; ++k) {\n"
+						          "\t\t\tconst lol_u32 row = (list >> (8 * k)) & 0xffu;\n"
+						          "\t\t\tif (row == 0xffu)\n\t\t\t\tbreak;\n"
+						          "\t\t\tconst lol_u32* c = lol_run%d + row * LOL_RUN%d_STRIDE;\n"
+						          "\t\t\tif (retest && lol_box_skips(x, y, z, LOL_TF(c[0]), LOL_TF(c[1]), LOL_TF(c[2]), LOL_TF(c[3]), "
+						          "LOL_TF(c[4]), LOL_TF(c[5]), LOL_TF(c[6]), best))\n\t\t\t\tcontinue;\n"
+						          "\t\t\tretest = round == 0;\n"
+						          "\t\t\t++nev;\n",
+						          run_no, run_no);
+					}
+					/* row = box (C, H, M), object id, then the object's own constants */
+					r.out = &sink;
+					for (int b = 0; b < LOL_BOUND_SLOTS; b++)
+						cst(&r, boxes[order[q]][b]);
+					cst_raw(&r, k + 1);
+					r.out = real_out;
+					free(sink.p);
+					if (q == 0)
+						sb_printf(&body, "\t\t\tconst lol_u32 oid = c[%d];\n", LOL_BOUND_SLOTS);
+					int t = emit_object(&r, s->objects[k]);
+					if (q == 0)
+						sb_printf(&body,
+						          "\t\t\tif (t%d < best || (t%d == best && oid < bid)) {\n"
+						          "\t\t\t\tbest = t%d;\n\t\t\t\tbid = oid;\n\t\t\t\twrow = row;\n\t\t\t}\n\t\t}\n"
+						          "\t\tif (round == 1)\n\t\t\tbreak;\n"
+						          "\t\t// every row outside the candidates still fails its box test here: done\n"
+						          "\t\tif (near_ok && nr.room > LOL_F(0x3f808312 /*1.004*/) * fabsf(best))\n\t\t\tbreak;\n"
+						          "\t\t// look at every row again (tests only): the rows that cannot be skipped now, and how far\n"
+						          "\t\t// the nearest skipped one is\n"
+						          "\t\tfloat room = LOL_INF;\n"
+						          "\t\tlol_u32 nc = 0xffffffffu, nn = 0u;\n"
+						          "#pragma unroll 1\n"
+						          "\t\tfor (int g = 0; g < %u; ++g) {\n"
+						          "\t\t\tconst lol_u32* gc = lol_run%d_groups + g * %d;\n"
+						          "\t\t\tconst float gq2 = lol_box_q2(x, y, z, LOL_TF(gc[0]), LOL_TF(gc[1]), LOL_TF(gc[2]), LOL_TF(gc[3]), "
+						          "LOL_TF(gc[4]), LOL_TF(gc[5]));\n"
+						          "\t\t\tif (lol_q2_skips(gq2, LOL_TF(gc[6]), best)) {\n"
+						          "\t\t\t\troom = fminf(room, lol_box_gap(gq2, LOL_TF(gc[6])));\n\t\t\t\tcontinue;\n\t\t\t}\n"
+						          "\t\t\tconst int last = (g + 1) * %u <= %u ? (g + 1) * %u : %u;\n"
+						          "#pragma unroll 1\n"
+						          "\t\t\tfor (int i = g * %u; i < last; ++i) {\n"
+						          "\t\t\t\tconst lol_u32* ct = lol_run%d + i * LOL_RUN%d_STRIDE;\n"
+						          "\t\t\t\tconst float q2 = lol_box_q2(x, y, z, LOL_TF(ct[0]), LOL_TF(ct[1]), LOL_TF(ct[2]), LOL_TF(ct[3]), "
+						          "LOL_TF(ct[4]), LOL_TF(ct[5]));\n"
+						          "\t\t\t\tif (lol_q2_skips(q2, LOL_TF(ct[6]), best)) {\n"
+						          "\t\t\t\t\troom = fminf(room, lol_box_gap(q2, LOL_TF(ct[6])));\n\t\t\t\t\tcontinue;\n\t\t\t\t}\n"
+						          "\t\t\t\tif (nn < 4u)\n"
+						          "\t\t\t\t\tnc = (nc & ~(0xffu << (8u * nn))) | ((lol_u32)i << (8u * nn));\n"
+						          "\t\t\t\t++nn;\n"
+						          "\t\t\t}\n\t\t}\n"
+						          "\t\tif (nn > 4u) { // more rows than the memory holds: the long way, and forget\n"
+						          "\t\t\tslow = true;\n\t\t\tbreak;\n\t\t}\n"
+						          "\t\tnr.cand = nc;\n\t\tnr.room = room;\n"
+						          "\t\t// the new candidates that round 0 did not evaluate\n"
+						          "\t\tlist = 0xffffffffu;\n"
+						          "\t\tlol_u32 nl = 0u;\n"
+						          "#pragma unroll\n"
+						          "\t\tfor (int k = 0; k < 4; ++k) {\n"
+						          "\t\t\tconst lol_u32 row = (nc >> (8 * k)) & 0xffu;\n"
+						          "\t\t\tif (row != 0xffu && !lol_near_has(list0, row)) {\n"
+						          "\t\t\t\tlist = (list & ~(0xffu << (8u * nl))) | (row << (8u * nl));\n"
+						          "\t\t\t\t++nl;\n\t\t\t}\n\t\t}\n"
+						          "\t\tif (nl == 0u)\n\t\t\tbreak;\n"
+						          "\t\tretest = false;\n"
+						          "\t}\n"
+						          "\tif (slow) {\n"
+						          "\t\tlol_near_reset(nr);\n"
+						          "\t\tconst lol_u64 r = lol_sdf_slow(x, y, z);\n"
+						          "\t\tid = (lol_u32)(r >> 32);\n"
+						          "\t\treturn __uint_as_float((lol_u32)r);\n"
+						          "\t}\n"
+						          "\tif (wrow != 0xffu)\n\t\tnr.cand = lol_near_front(nr.cand, wrow);\n"
+						          "\tlol_count_skip((%uu - nev) * %uu);\n"
+						          "\t}\n",
+						          t, t, t, ngroups, run_no, LOL_BOUND_SLOTS,
+						          LOL_GROUP, n, LOL_GROUP, n, LOL_GROUP, run_no, run_no,
+						          n, cost);
+				} else if (worklist) {
 					/* Per-lane work lists.  The plain loops below walk groups and members with a
 					 * warp-uniform index: every lane tests, and the warp then evaluates the UNION of
 					 * what its lanes could not skip (21 of 32 lanes per instruction on the
@@ -1421,10 +1536,6 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\t\tif (t%d < best || (t%d == best && oid < bid)) {\n"
 						          "\t\t\t\tbest = t%d;\n\t\t\t\tbid = oid;\n\t\t\t}\n\t\t}\n\t}\n\t}\n",
 						          t, t, t);
-					/* a stride of 4 x odd words: rows read with per-lane addresses fall into different
-					 * 16-byte bank groups unless their numbers agree modulo 8 (Morton neighbours do not) */
-					while ((r.nrow / 4) % 2 == 0)
-						row_push(&r, 0.f);
 				} else {
 				if (q == 0) {
 						sb_printf(&body, "\t{\n");
@@ -1502,6 +1613,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\t\t\tbest = t%d;\n\t\t\t\tbid = oid;\n\t\t\t}\n\t\t}\n\t}\n\t}\n",
 						          t, t, t);
 				}
+					if (lol_pad_rows)
+						while ((r.nrow / 4) % 2 == 0)
+							row_push(&r, 0.f);
 					if (q == 0)
 						per_row = r.nrow;
 					sb_printf(&tables.words, "\n\t");
@@ -1537,12 +1651,12 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		sb_printf(&body,
 		          "\t// The fast forms are bit-identical to IEEE sqrt / division only inside\n"
 		          "\t// these ranges (DESIGN.md, guarded fast path); outside, redo it the long way.\n"
-		          "\tif (!(lo >= LOL_SQRT_FAST_MIN)) {\n"
+		          "\tif (!(lo >= LOL_SQRT_FAST_MIN)) {\n%s"
 		          "\t\tconst lol_u64 r = %s(x, y, z);\n"
 		          "\t\tid = (lol_u32)(r >> 32);\n"
 		          "\t\treturn __uint_as_float((lol_u32)r);\n"
 		          "\t}\n",
-		          fallback);
+		          lol_emit_near ? "\t\tlol_near_reset(nr); // whatever was decided with out-of-range values\n" : "", fallback);
 	if (two)
 		;
 	else if (packed_ret)
@@ -1705,10 +1819,39 @@ static int guard_pays(const lolb200_scene* s) {
 	return unions >= 1 || spheres >= 3;
 }
 
+/* One pruned table loop of at most 254 rows, and nothing else looped: the shape the per-ray candidate
+ * memory handles (row numbers are bytes, 0xff = none). */
+static int single_pruned_run(const lolb200_scene* s, int threshold) {
+	int runs = 0, ok = 1;
+	char** sigs = calloc(s->n_objects ? s->n_objects : 1, sizeof *sigs);
+	for (uint32_t i = 0; i < s->n_objects; i++) {
+		struct sb sig = {0};
+		signature(s, s->objects[i], &sig);
+		sigs[i] = sig.p;
+	}
+	for (uint32_t i = 0; i < s->n_objects;) {
+		uint32_t j = i + 1;
+		while (j < s->n_objects && strcmp(sigs[j], sigs[i]) == 0)
+			j++;
+		if ((int)(j - i) >= threshold) {
+			runs++;
+			ok &= j - i <= 254u;
+		}
+		i = j;
+	}
+	for (uint32_t i = 0; i < s->n_objects; i++)
+		free(sigs[i]);
+	free(sigs);
+	return runs == 1 && ok;
+}
+
 static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
-                     int prune, int two, int smem_ok, int pack) {
+                     int prune, int two, int smem_ok, int pack, int near) {
 	struct sb tables = {0};
 	struct est_memo memo = {{0, 0}, {0, 0}, {NULL, NULL}};
+	near = near && prune && !two && single_pruned_run(s, loop_threshold);
+	lol_pad_rows = near || lol_worklist;
+	sb_printf(out, "#define LOL_NEAR %d\n", near);
 	if (guarded == 1 && !guard_pays(s) && !two)
 		guarded = 0;
 	if (guarded && constants_in_range(s)) {
@@ -1723,6 +1866,14 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		if (two)
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf2", "__forceinline__", 1, div_ok,
 			            "lol_sdf_ref", prune, 1, smem_ok, &memo, 0, pack, div_ok);
+		if (near) {
+			/* the candidate memory's way out when more rows survive than it holds: the IEEE function */
+			sb_printf(out, "#define lol_sdf_slow lol_sdf_ref\n");
+			lol_emit_near = 1;
+			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf_nr", "__forceinline__", 1, div_ok,
+			            "lol_sdf_ref", prune, 0, smem_ok, &memo, pack, pack, div_ok);
+			lol_emit_near = 0;
+		}
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
@@ -1731,7 +1882,18 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
+		if (near) {
+			sb_printf(out,
+			          "// the candidate memory's way out when more rows survive than it holds\n"
+			          "__device__ __noinline__ lol_u64 lol_sdf_slow(const float x, const float y, const float z) {\n"
+			          "\tlol_u32 id;\n\tconst float d = lol_sdf(x, y, z, 0u, id);\n"
+			          "\treturn ((lol_u64)id << 32) | (lol_u64)__float_as_uint(d);\n}\n");
+			lol_emit_near = 1;
+			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf_nr", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, 0, 0);
+			lol_emit_near = 0;
+		}
 	}
+	lol_pad_rows = 0;
 	free(tables.p);
 	free(memo.own[0]);
 	free(memo.own[1]);
@@ -2050,8 +2212,11 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		else
 			sb_printf(&out, "#define LOL_LAUNCH_BOUNDS __launch_bounds__(%d)\n", threads);
 		sb_printf(&out, "#define LOL_ROLL_PHASES %d\n", o.roll_phases != 0);
-		/* default: unrolled until measured otherwise */
-		sb_printf(&out, "#define LOL_ROLL_V1 %d\n", o.roll_v1 < 0 ? LOLB200_DEFAULT_ROLL_V1 : o.roll_v1);
+		/* default: straight-line scenes unrolled (rolled: scene4 +0.8 % / +2.5 %), table-loop scenes rolled
+		 * (their distance code is long: 1024 spheres 43.8 -> 43.2 ms, and the per-ray candidate memory
+		 * adds to every copy) -- measured on B200, DESIGN.md */
+		sb_printf(&out, "#define LOL_ROLL_V1 %d\n",
+		          o.roll_v1 < 0 ? (has_table_loop(s, threshold) ? 2 : LOLB200_DEFAULT_ROLL_V1) : o.roll_v1);
 	}
 	if (variant == 2) {
 		/* struct lol_warp_smem (lol_kernel.cuh): p, n, t|px, dir, sh[lights], id,
@@ -2075,7 +2240,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		emit_child_materials(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
 	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */,
-	         o.pack_pairs);
+	         o.pack_pairs, variant == 1 && (o.near_cache < 0 ? 1 : o.near_cache));
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

@@ -102,6 +102,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->share_first_step = 1;
 	o->roll_v1 = -1;
 	o->loop_worklist = -1;
+	o->near_cache = -1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

@@ -677,3 +677,25 @@ def test_config_c2_at_1920x1080_through_the_unmodified_render_thread(name, scene
     assert err.max() <= 1
     assert err[got["id"] == 0].max() == 0
     got["renderer"].close()
+
+
+@pytest.mark.parametrize("name", ["synthetic", "synthetic_csg"])
+def test_candidate_memory_4k_bit_identical(name):
+    """options.near_cache (the per-ray candidate memory of pruned table loops, lol_kernel.cuh: struct lol_near)
+    on and off at 3840x2160: the SAME frame, distances, ids, primary and shadow step counts and evaluation
+    counters; and far fewer FLOPs skipped by box tests that are never made."""
+    import loltracer_b200 as lb
+    from loltracer_b200 import scenegen
+
+    w, h = 3840, 2160
+    scene = lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name.endswith("csg")))
+    a = _render(lb, scene, w, h, options=lb.Options.default(variant=1, near_cache=0, counters=1))
+    b = _render(lb, scene, w, h, options=lb.Options.default(variant=1, near_cache=1, counters=1))
+    assert "#define LOL_NEAR 1" in b["renderer"].source and "#define LOL_NEAR 0" in a["renderer"].source
+    for key in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+    ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
+    assert {k: v for k, v in ca.items() if k != "skipped_flops"} == {k: v for k, v in cb.items() if k != "skipped_flops"}
+    a["renderer"].close()
+    b["renderer"].close()

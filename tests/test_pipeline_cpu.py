@@ -241,3 +241,50 @@ def test_shadow_early_out_is_refused_for_non_finite_scene_constants():
     s = ok.struct
     s.nodes[0].radius = float("inf")
     assert "#define LOL_SHADOW_EARLY 0" in lb.lower_cuda(ok, lb.Options.default(variant=1))
+
+
+# ---- the per-ray candidate memory of pruned table loops (lol_kernel.cuh: struct lol_near) -------------
+
+def _near_scene(kind):
+    """Scenes with ONE pruned table loop: the 1024-sphere scene; a crowd of overlapping equal spheres (more
+    than four rows within reach at once: the memory overflows and the evaluation goes the long way); a
+    sparse row of spheres (long stretches where nothing but the floor is near)."""
+    from loltracer_b200 import scenegen
+    from test_lowering_fuzz import HEAD
+
+    if kind == "synthetic":
+        return scenegen.synthetic_scene_text()
+    rng = np.random.default_rng(77)
+    if kind == "crowd":
+        objs = [f"sphere {{ material = #{1 + i % 2}, point = ({rng.uniform(-1.5, 1.5):.3f},{rng.uniform(0.2, 2.2):.3f},"
+                f"{rng.uniform(-6.5, -4.5):.3f}), radius = {rng.uniform(0.8, 1.4):.3f} }}" for i in range(24)]
+    else:
+        objs = [f"sphere {{ material = #{1 + i % 2}, point = ({-14 + 1.5 * i:.3f},{0.5 + 0.1 * (i % 3):.3f},"
+                f"{-6 - (i % 5):.3f}), radius = 0.45 }}" for i in range(20)]
+    return HEAD + ",\n".join(objs + ["plane { material = #2, y = -0.5 }"]) + " }"
+
+
+@pytest.mark.parametrize("kind", ["synthetic", "crowd", "sparse"])
+def test_candidate_memory_of_pruned_loops_is_exact(kind, tmp_path):
+    """options.near_cache: a ray remembers the rows it could not skip and how far it may move before the others
+    must be looked at again.  With it and without it: the oracle's frame, distances, ids and step counts (RGB
+    exact on the host), also where the memory overflows (crowd) and with every shortcut off."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_string(_near_scene(kind))
+    w, h = (64, 36) if kind == "synthetic" else (96, 54)
+    want = ol.port_render(scene, w, h, counts=True)
+    for tag, kw in (("on", dict(near_cache=1)), ("off", dict(near_cache=0)),
+                    ("ieee", dict(near_cache=1, guarded_fastpath=0, pack_pairs=0)),
+                    ("noskip", dict(near_cache=1, skip_black_miss=0, cull_backfacing=0, shadow_early_out=0))):
+        src = lb.lower_cuda(scene, lb.Options.default(variant=1, loop_threshold=8, **kw))
+        assert f"#define LOL_NEAR {int(kw['near_cache'])}" in src
+        L = ol.cpu_pipeline(tmp_path, src, f"near_{kind}_{tag}")
+        _same(ol.cpu_pipeline_render(L, lb, scene, w, h), want, shadow_counts=(tag == "noskip"))
+    # cameras inside the crowd, far away (beyond the coordinate range the memory trusts) and NaN
+    cams = [lb.Camera.make([0, 1, -5.5], [0.2, -0.1, -1], 1.5), lb.Camera.make([0, 2, 900], [0, 0, -1], 0.3),
+            lb.Camera.make([0, 5, -6], [0, -1, 0], 1.5)]
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, loop_threshold=8, near_cache=1))
+    L = ol.cpu_pipeline(tmp_path, src, f"near_{kind}_cams")
+    for cam in cams:
+        _same(ol.cpu_pipeline_render(L, lb, scene, 48, 27, camera=cam), ol.port_render(scene, 48, 27, camera=cam, counts=True))
