@@ -1341,18 +1341,22 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				const char* best_args = two ? "bestA, bestB" : "best";
 				const char* sfx = two ? "2" : "";
 				if (lol_emit_near && !two && !packed_ret) {
-					/* The per-ray candidate memory (lol_kernel.cuh: struct lol_near).  Round 0 evaluates the
-					 * remembered candidates (the last winner first); if the room the ray had is used up,
-					 * every row is looked at again -- tests only -- which gives the rows that cannot be
-					 * skipped now (the new candidates) and the distance to the nearest skipped one (the new
-					 * room); round 1 evaluates the new candidates that round 0 did not.  ONE copy of the
-					 * object's code serves both rounds. */
+					/* The per-ray candidate memory (lol_kernel.cuh: struct lol_near).  The remembered
+					 * candidates are evaluated first (the last winner untested, the others behind their
+					 * box test).  If the room the ray had is used up, every row is looked at again --
+					 * tests only, out of line (lol_near_collect) -- which gives the rows that cannot be
+					 * skipped now and the distance to the nearest skipped one; the new candidates that
+					 * were not evaluated yet are evaluated by the SAME copy of the object's code.  More
+					 * than four survivors (a ray's first call knows only the floor's distance, or a
+					 * crowd): the evaluation goes the long way (lol_sdf_slow) and the rows are looked at
+					 * once more with its exact result, which leaves the few that really matter. */
 					const unsigned cost = node_cost(s, s->objects[i]) + 1u;
 					struct sb* const real_out = r.out;
 					struct sb sink = {0};
 					if (q == 0) {
 						sb_printf(&body,
 						          "\t{\n"
+						          "\tLOL_NEAR_STAT(0, 1);\n"
 						          "\tnr.room -= lol_fma(move, LOL_F(0x3f800347 /*1.0001*/), LOL_NEAR_PAD);\n"
 						          "\tconst bool near_ok = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= LOL_NEAR_COORD;\n"
 						          "\tconst lol_u32 list0 = nr.cand;\n"
@@ -1390,30 +1394,12 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\tif (round == 1)\n\t\t\tbreak;\n"
 						          "\t\t// every row outside the candidates still fails its box test here: done\n"
 						          "\t\tif (near_ok && nr.room > LOL_F(0x3f808312 /*1.004*/) * fabsf(best))\n\t\t\tbreak;\n"
-						          "\t\t// look at every row again (tests only): the rows that cannot be skipped now, and how far\n"
-						          "\t\t// the nearest skipped one is\n"
-						          "\t\tfloat room = LOL_INF;\n"
-						          "\t\tlol_u32 nc = 0xffffffffu, nn = 0u;\n"
-						          "#pragma unroll 1\n"
-						          "\t\tfor (int g = 0; g < %u; ++g) {\n"
-						          "\t\t\tconst lol_u32* gc = lol_run%d_groups + g * %d;\n"
-						          "\t\t\tconst float gq2 = lol_box_q2(x, y, z, LOL_TF(gc[0]), LOL_TF(gc[1]), LOL_TF(gc[2]), LOL_TF(gc[3]), "
-						          "LOL_TF(gc[4]), LOL_TF(gc[5]));\n"
-						          "\t\t\tif (lol_q2_skips(gq2, LOL_TF(gc[6]), best)) {\n"
-						          "\t\t\t\troom = fminf(room, lol_box_gap(gq2, LOL_TF(gc[6])));\n\t\t\t\tcontinue;\n\t\t\t}\n"
-						          "\t\t\tconst int last = (g + 1) * %u <= %u ? (g + 1) * %u : %u;\n"
-						          "#pragma unroll 1\n"
-						          "\t\t\tfor (int i = g * %u; i < last; ++i) {\n"
-						          "\t\t\t\tconst lol_u32* ct = lol_run%d + i * LOL_RUN%d_STRIDE;\n"
-						          "\t\t\t\tconst float q2 = lol_box_q2(x, y, z, LOL_TF(ct[0]), LOL_TF(ct[1]), LOL_TF(ct[2]), LOL_TF(ct[3]), "
-						          "LOL_TF(ct[4]), LOL_TF(ct[5]));\n"
-						          "\t\t\t\tif (lol_q2_skips(q2, LOL_TF(ct[6]), best)) {\n"
-						          "\t\t\t\t\troom = fminf(room, lol_box_gap(q2, LOL_TF(ct[6])));\n\t\t\t\t\tcontinue;\n\t\t\t\t}\n"
-						          "\t\t\t\tif (nn < 4u)\n"
-						          "\t\t\t\t\tnc = (nc & ~(0xffu << (8u * nn))) | ((lol_u32)i << (8u * nn));\n"
-						          "\t\t\t\t++nn;\n"
-						          "\t\t\t}\n\t\t}\n"
-						          "\t\tif (nn > 4u) { // more rows than the memory holds: the long way, and forget\n"
+						          "\t\t// look at every row again (tests only, out of line)\n"
+						          "\t\tLOL_NEAR_STAT(1, 1);\n"
+						          "\t\tconst lol_u64 seen = lol_near_collect(x, y, z, best);\n"
+						          "\t\tconst lol_u32 nc = (lol_u32)(seen & 0xffffffffull);\n"
+						          "\t\tconst float room = __uint_as_float((lol_u32)(seen >> 32));\n"
+						          "\t\tif (!(room >= 0.f)) { // more than four rows cannot be skipped: the plain loop, out of line\n"
 						          "\t\t\tslow = true;\n\t\t\tbreak;\n\t\t}\n"
 						          "\t\tnr.cand = nc;\n\t\tnr.room = room;\n"
 						          "\t\t// the new candidates that round 0 did not evaluate\n"
@@ -1428,18 +1414,21 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\tif (nl == 0u)\n\t\t\tbreak;\n"
 						          "\t\tretest = false;\n"
 						          "\t}\n"
+						          "\tLOL_NEAR_STAT(3, nev);\n"
 						          "\tif (slow) {\n"
-						          "\t\tlol_near_reset(nr);\n"
-						          "\t\tconst lol_u64 r = lol_sdf_slow(x, y, z);\n"
+						          "\t\tLOL_NEAR_STAT(2, 1);\n"
+						          "\t\t// many rows matter here (open space beside a crowd): the plain pruned loop handles that best --\n"
+						          "\t\t// it tightens `best` as it goes.  The ray keeps the winner and looks again at its next point.\n"
+						          "\t\tconst lol_u64 r = lol_sdf_slow(x, y, z, bid);\n"
 						          "\t\tid = (lol_u32)(r >> 32);\n"
+						          "\t\tnr.room = -LOL_INF;\n"
+						          "\t\tnr.cand = (id >= %uu && id < %uu) ? (0xffffff00u | lol_run%d_rowof[id - %uu]) : 0xffffffffu;\n"
 						          "\t\treturn __uint_as_float((lol_u32)r);\n"
 						          "\t}\n"
 						          "\tif (wrow != 0xffu)\n\t\tnr.cand = lol_near_front(nr.cand, wrow);\n"
 						          "\tlol_count_skip((%uu - nev) * %uu);\n"
 						          "\t}\n",
-						          t, t, t, ngroups, run_no, LOL_BOUND_SLOTS,
-						          LOL_GROUP, n, LOL_GROUP, n, LOL_GROUP, run_no, run_no,
-						          n, cost);
+						          t, t, t, i + 1, j + 1, run_no, i + 1, n, cost);
 				} else if (worklist) {
 					/* Per-lane work lists.  The plain loops below walk groups and members with a
 					 * warp-uniform index: every lane tests, and the warp then evaluates the UNION of
@@ -1624,7 +1613,8 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					cgen_release(&r);
 					free(scratch.p);
 				}
-				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n", run_no, per_row);
+				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n#define LOL_RUN%d_ROWS %u\n#define LOL_RUN%d_GROUP %u\n",
+				          run_no, per_row, run_no, n, run_no, LOL_GROUP);
 				run_no++;
 				free(boxes);
 				free(order);
@@ -1819,6 +1809,49 @@ static int guard_pays(const lolb200_scene* s) {
 	return unions >= 1 || spheres >= 3;
 }
 
+static const char lol_sdf_slow_text[] =
+	"// the candidate memory's way out when more rows matter than it holds: ONE out-of-line copy of the plain function\n"
+	"__device__ __noinline__ lol_u64 lol_sdf_slow(const float x, const float y, const float z, const lol_u32 hint) {\n"
+	"\tlol_u32 id;\n\tconst float d = lol_sdf(x, y, z, hint, id);\n"
+	"\treturn ((lol_u64)id << 32) | (lol_u64)__float_as_uint(d);\n}\n";
+
+static const char lol_near_collect_text[] =
+	"// Every row of the pruned table loop against `best`, tests only (lol_kernel.cuh: struct lol_near): the rows\n"
+	"// that cannot be skipped (the first four, one per byte of the low word) and, in the high word, a lower bound of\n"
+	"// min over the skipped rows of  dbox(p) - m1  -- how far the point may move before a skipped row has to be\n"
+	"// looked at again (+INF: none skipped); -1 when more than four rows cannot be skipped (an incomplete look).\n"
+	"__device__ __noinline__ lol_u64 lol_near_collect(const float x, const float y, const float z, const float best) {\n"
+	"\tfloat room = LOL_INF;\n"
+	"\tlol_u32 nc = 0xffffffffu, nn = 0u;\n"
+	"#pragma unroll 1\n"
+	"\tfor (int g = 0; g * LOL_RUN0_GROUP < LOL_RUN0_ROWS; ++g) {\n"
+	"\t\tconst lol_u32* gc = lol_run0_groups + g * 7;\n"
+	"\t\tconst float gq2 = lol_box_q2(x, y, z, LOL_TF(gc[0]), LOL_TF(gc[1]), LOL_TF(gc[2]), LOL_TF(gc[3]), LOL_TF(gc[4]), LOL_TF(gc[5]));\n"
+	"\t\tif (lol_q2_skips(gq2, LOL_TF(gc[6]), best)) {\n"
+	"\t\t\troom = fminf(room, lol_box_gap(gq2, LOL_TF(gc[6])));\n"
+	"\t\t\tcontinue;\n"
+	"\t\t}\n"
+	"\t\tconst int last = (g + 1) * LOL_RUN0_GROUP <= LOL_RUN0_ROWS ? (g + 1) * LOL_RUN0_GROUP : LOL_RUN0_ROWS;\n"
+	"#pragma unroll 1\n"
+	"\t\tfor (int i = g * LOL_RUN0_GROUP; i < last; ++i) {\n"
+	"\t\t\tconst lol_u32* ct = lol_run0 + i * LOL_RUN0_STRIDE;\n"
+	"\t\t\tconst float q2 = lol_box_q2(x, y, z, LOL_TF(ct[0]), LOL_TF(ct[1]), LOL_TF(ct[2]), LOL_TF(ct[3]), LOL_TF(ct[4]), LOL_TF(ct[5]));\n"
+	"\t\t\tif (lol_q2_skips(q2, LOL_TF(ct[6]), best)) {\n"
+	"\t\t\t\troom = fminf(room, lol_box_gap(q2, LOL_TF(ct[6])));\n"
+	"\t\t\t\tcontinue;\n"
+	"\t\t\t}\n"
+	"\t\t\tif (nn < 4u)\n"
+	"\t\t\t\tnc = (nc & ~(0xffu << (8u * nn))) | ((lol_u32)i << (8u * nn));\n"
+	"\t\t\t++nn;\n"
+	"\t\t}\n"
+	"\t}\n"
+	"\tif (nn > 4u) // an incomplete look: the low word holds the first four survivors\n"
+	"\t\troom = -1.f;\n"
+	"\telse if (!(room >= 0.f))\n"
+	"\t\troom = 0.f; // a skipped row right at its margin: no room, but the look is complete\n"
+	"\treturn (lol_u64)nc | ((lol_u64)__float_as_uint(room) << 32);\n"
+	"}\n";
+
 /* One pruned table loop of at most 254 rows, and nothing else looped: the shape the per-ray candidate
  * memory handles (row numbers are bytes, 0xff = none). */
 static int single_pruned_run(const lolb200_scene* s, int threshold) {
@@ -1867,11 +1900,13 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf2", "__forceinline__", 1, div_ok,
 			            "lol_sdf_ref", prune, 1, smem_ok, &memo, 0, pack, div_ok);
 		if (near) {
-			/* the candidate memory's way out when more rows survive than it holds: the IEEE function */
-			sb_printf(out, "#define lol_sdf_slow lol_sdf_ref\n");
+			sb_printf(out, "%s", lol_sdf_slow_text);
+			sb_putn(out, lol_near_collect_text, strlen(lol_near_collect_text));
 			lol_emit_near = 1;
+			sb_printf(out, "#define lol_pairc lol_pairc_nr // this form's own pair constants\n");
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf_nr", "__forceinline__", 1, div_ok,
 			            "lol_sdf_ref", prune, 0, smem_ok, &memo, pack, pack, div_ok);
+			sb_printf(out, "#undef lol_pairc\n");
 			lol_emit_near = 0;
 		}
 		free(ref.p);
@@ -1883,11 +1918,8 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		sb_putn(out, fn.p, fn.len);
 		free(fn.p);
 		if (near) {
-			sb_printf(out,
-			          "// the candidate memory's way out when more rows survive than it holds\n"
-			          "__device__ __noinline__ lol_u64 lol_sdf_slow(const float x, const float y, const float z) {\n"
-			          "\tlol_u32 id;\n\tconst float d = lol_sdf(x, y, z, 0u, id);\n"
-			          "\treturn ((lol_u64)id << 32) | (lol_u64)__float_as_uint(d);\n}\n");
+			sb_printf(out, "%s", lol_sdf_slow_text);
+			sb_putn(out, lol_near_collect_text, strlen(lol_near_collect_text));
 			lol_emit_near = 1;
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf_nr", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, 0, 0);
 			lol_emit_near = 0;

@@ -44,7 +44,10 @@ def test_deferred_rays_4k_bit_identical_to_variant1(name, caps, scenes_dir):
     assert "#define LOL_VARIANT 4" in b["renderer"].source
     _same(a, b)
     ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
-    assert ca == cb, (ca, cb)
+    # (what the box tests skipped is not compared: variant 1 marches table-loop scenes with the per-ray
+    # candidate memory, variant 4 with the plain loops -- different tests made, the same rows' results)
+    drop = lambda c: {k: v for k, v in c.items() if k != "skipped_flops"}
+    assert drop(ca) == drop(cb), (ca, cb)
     a["renderer"].close()
     b["renderer"].close()
 

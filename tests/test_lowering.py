@@ -277,7 +277,9 @@ def test_packed_pairs_structure(scenes_dir):
 
     def fast_fn(src):
         body = src.split("//@@SCENE@@")[0]
-        return body[body.index("__forceinline__ float lol_sdf("):]
+        body = body[body.index("__forceinline__ float lol_sdf("):]
+        # (programs with one pruned table loop carry a second form behind it: lol_sdf_slow / lol_sdf_nr)
+        return body.split("// the candidate memory's way out")[0]
 
     s4 = lb.Scene.from_file(os.path.join(scenes_dir, "scene4.lol"))
     f = fast_fn(lb.lower_cuda(s4, lb.Options.default(pack_pairs=2)))
