@@ -239,6 +239,13 @@ typedef struct lolb200_options {
 	                            march steps evaluate the candidates and walk no group box
 	                            at all (lol_kernel.cuh: struct lol_near; exact).
 	                            1 = on, 0 = off, -1 = default (on)                   */
+	int32_t guard_out;          /* variant 1 with the guarded forms: the march loops run the guarded
+	                            arithmetic alone and leave the loop when the range guard
+	                            fails; that one step is taken with the IEEE forms and the
+	                            loop entered again -- the fall-back call and its
+	                            reconvergence point are no longer part of every step
+	                            (exact: same evaluations, same order).
+	                            1 = on, 0 = off, -1 = default (on)                   */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

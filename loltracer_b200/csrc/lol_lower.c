@@ -117,6 +117,7 @@ struct cgen {
 	size_t npairs;
 	struct pairc* pc;    /* where constant pairs of straight-line code go */
 	const char* indent;
+	int first_free;      /* guarded single-ray form: nothing was evaluated yet, `best` is still +INF (emit_straight_object) */
 };
 
 static void row_push(struct cgen* g, float v) {
@@ -515,7 +516,7 @@ static int emit_node(struct cgen* g, uint32_t idx) {
 			if (g->two)
 				sb_printf(g->out, "%slo = lol_min_halves(lo, s%d);\n", g->indent, me);
 			else
-				sb_printf(g->out, "%slo = fminf(lo, s%d);\n", g->indent, me);
+				sb_printf(g->out, "%slo = lol_min_nan(lo, s%d);\n", g->indent, me);
 			sb_printf(g->out, "%sconst %s t%d = lol_sqrt_fast%s(s%d) - ", g->indent, T, me,
 			          g->two ? "2" : "", me);
 			ncst(g, idx, F_R);
@@ -999,7 +1000,14 @@ static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, co
 		          "%sif (a_ < bestA%s) {\n%s\tbestA = a_;\n%s\tbidA = %uu;\n%s}\n"
 		          "%sif (b_ < bestB%s) {\n%s\tbestB = b_;\n%s\tbidB = %uu;\n%s}\n",
 		          ind, t, t, ind, tA, ind, ind, k + 1, ind, ind, tB, ind, ind, k + 1, ind);
-	} else if (tie_aware)
+	} else if (g->first_free && g->fast && g->div_ok && !own_box && tabs[1] == '\0')
+		/* The first object of the guarded form, outside every test: `best` is still +INF, and the
+		 * result of this function only counts when its range guard passes -- coordinates and every
+		 * scene constant at most 2^60, no NaN -- where an object's distance is finite (sums,
+		 * products and square roots of values below 2^123; quotients by a proved constant), so
+		 * `t < +INF` holds.  The update is unconditional, and the compiler then knows `bid`. */
+		sb_printf(body, "%sbest = t%d; // first object: t < +INF under the range guard\n%sbid = %uu;\n", ind, t, ind, k + 1);
+	else if (tie_aware)
 		sb_printf(body, "%sif (t%d < best || (t%d == best && %uu < bid)) {\n%s\tbest = t%d;\n%s\tbid = %uu;\n%s}\n",
 		          ind, t, t, k + 1, ind, t, ind, k + 1, ind);
 	else
@@ -1009,6 +1017,7 @@ static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, co
 		sb_printf(body, "%s\t} else\n%s\t\tlol_count_skip(%uu);\n", tabs, tabs,
 		          (node_cost(g->s, g->s->objects[k]) + 1u) * (two ? 2u : 1u));
 	sb_printf(body, "%s}\n", tabs);
+	g->first_free = 0;
 }
 
 /* The decisions of the sampled estimate, kept for the other distance functions of
@@ -1084,6 +1093,8 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 	/* The out-of-line fallback hands (distance, id) back in one 64-bit register
 	 * pair; a reference parameter would force the caller's id onto the stack. */
 	const int packed_ret = strcmp(name, "lol_sdf") != 0 && strcmp(name, "lol_sdf_nr") != 0 && !two; /* (distance, id) in one 64-bit value */
+	/* the guarded single-ray function comes in two pieces: the arithmetic (lol_sdf_try) and the fall-back around it */
+	const int split_guard = fast && !two && !packed_ret && !lol_emit_near;
 	sb_printf(&body,
 	          "// sdf (naive_renderer.c:30-44): running strict-< minimum over the top-level\n"
 	          "// objects, ids 1..n in file order, (INF, 0) when nothing is closer.\n");
@@ -1110,6 +1121,17 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "                                         lol_near& nr, const float move, lol_u32& id) {\n"
 		          "\tconst lol_u32 hint = 0u;\n",
 		          attrs, name);
+	else if (split_guard)
+		sb_printf(&body,
+		          "// The guarded form WITHOUT its fall-back: the caller is told whether the guard passed (`ok`), and\n"
+		          "// the result only counts when it did.  lol_sdf() below is the complete function; the march\n"
+		          "// loops of variant 1 call this one and leave the loop when the guard fails (LOL_GUARD_OUT), so\n"
+		          "// the out-of-line call and its reconvergence point are not part of every step.\n"
+		          "// hint: an object id worth evaluating first (the ray's last winner), 0 = none; only\n"
+		          "// table loops use it, and it never changes the result.\n"
+		          "__device__ %s float %s_try(const float x, const float y, const float z,\n"
+		          "                                         const lol_u32 hint, lol_u32& id, bool& ok) {\n",
+		          attrs, name);
 	else
 		sb_printf(&body,
 		          "// hint: an object id worth evaluating first (the ray's last winner), 0 = none; only\n"
@@ -1123,8 +1145,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		sb_printf(&body, "\tfloat best = LOL_INF;\n\tlol_u32 bid = 0u;\n");
 	if (fast && !two)
 		sb_printf(&body,
-		          "\t// One range guard per evaluation: lo = min(every sqrt argument, 2^60 - max|p|).\n"
-		          "\tfloat lo = LOL_COORD_MAX - fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));\n");
+		          "\t// One range guard per evaluation: lo = min(every sqrt argument, 2^60 - max|p|), with a minimum\n"
+		          "\t// and a maximum that hand a NaN on (min.NaN / max.NaN): a NaN or infinite coordinate fails\n"
+		          "\t// the guard, so inside it every distance below is a finite number.\n"
+		          "\tfloat lo = LOL_COORD_MAX - lol_max_nan(lol_max_nan(fabsf(x), fabsf(y)), fabsf(z));\n");
 
 	/* Segments: maximal runs of same-shaped neighbours.  Long runs become table
 	 * loops.  With pruning the straight-line objects are evaluated FIRST (they
@@ -1167,6 +1191,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		struct sb* const real_body = g.out;
 		int any_test = 0;
 		g.out = &reordered;
+		g.first_free = fast && !two;
 		for (uint32_t k = 0; k < no; k++)
 			if (straight[k] == 1)
 				emit_straight_object(&reordered, &g, k, sigs[k], two, 0, NULL, "\t");
@@ -1241,6 +1266,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		free(boxes);
 		free(bounded);
 	}
+	g.first_free = fast && !two && straight_in_file_order;
 	for (int pass = 0; pass < 2; pass++)
 	for (uint32_t i = 0; i < s->n_objects;) {
 		uint32_t j = i + 1;
@@ -1257,6 +1283,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		if (is_loop) {
 			/* objects i .. j-1 share one shape: loop over a parameter table */
 			size_t per_row = 0;
+			g.first_free = 0;
 			const uint32_t n = j - i;
 			sb_printf(&body, "\t// objects %u..%u: %u x %s\n", i + 1, j, n, sigs[i]);
 			if (!prune) {
@@ -1637,6 +1664,23 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "\t\treturn lol_pk(__uint_as_float((lol_u32)rA), __uint_as_float((lol_u32)rB));\n"
 		          "\t}\n\tidA = bidA;\n\tidB = bidB;\n\treturn lol_pk(bestA, bestB);\n}\n",
 		          fallback, fallback);
+	else if (split_guard)
+		sb_printf(&body,
+		          "\tok = lo >= LOL_SQRT_FAST_MIN;\n\tid = bid;\n\treturn best;\n}\n"
+		          "// The complete guarded function.\n"
+		          "__device__ %s float %s(const float x, const float y, const float z,\n"
+		          "                                         const lol_u32 hint, lol_u32& id) {\n"
+		          "\tbool ok;\n"
+		          "\tconst float best = %s_try(x, y, z, hint, id, ok);\n"
+		          "\t// The fast forms are bit-identical to IEEE sqrt / division only inside\n"
+		          "\t// these ranges (DESIGN.md, guarded fast path); outside, redo it the long way.\n"
+		          "\tif (!ok) {\n"
+		          "\t\tconst lol_u64 r = %s(x, y, z);\n"
+		          "\t\tid = (lol_u32)(r >> 32);\n"
+		          "\t\treturn __uint_as_float((lol_u32)r);\n"
+		          "\t}\n"
+		          "\treturn best;\n}\n",
+		          attrs, name, name, fallback);
 	else if (fast)
 		sb_printf(&body,
 		          "\t// The fast forms are bit-identical to IEEE sqrt / division only inside\n"
@@ -1647,7 +1691,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		          "\t\treturn __uint_as_float((lol_u32)r);\n"
 		          "\t}\n",
 		          lol_emit_near ? "\t\tlol_near_reset(nr); // whatever was decided with out-of-range values\n" : "", fallback);
-	if (two)
+	if (two || split_guard)
 		;
 	else if (packed_ret)
 		sb_printf(&body, "\treturn ((lol_u64)bid << 32) | (lol_u64)__float_as_uint(best);\n}\n");
@@ -1879,7 +1923,7 @@ static int single_pruned_run(const lolb200_scene* s, int threshold) {
 }
 
 static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold, int guarded,
-                     int prune, int two, int smem_ok, int pack, int near) {
+                     int prune, int two, int smem_ok, int pack, int near, int guard_out) {
 	struct sb tables = {0};
 	struct est_memo memo = {{0, 0}, {0, 0}, {NULL, NULL}};
 	near = near && prune && !two && single_pruned_run(s, loop_threshold);
@@ -1891,6 +1935,8 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		struct sb ref = {0};
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
+		/* variant 1's march loops call lol_sdf_try and keep the guard's fall-back outside the loop */
+		sb_printf(out, "#define LOL_GUARD_OUT %d\n", guard_out && !near && !two);
 		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, pack, div_ok);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
@@ -1912,7 +1958,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		free(ref.p);
 	} else {
 		struct sb fn = {0};
-		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n");
+		sb_printf(out, "#define LOL_GUARDED 0\n#define LOL_DIV_CONST 0\n#define LOL_GUARD_OUT 0\n");
 		emit_sdf_fn(&fn, &tables, s, loop_threshold, "lol_sdf", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, 0, 0);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, fn.p, fn.len);
@@ -2272,7 +2318,8 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		emit_child_materials(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
 	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */,
-	         o.pack_pairs, variant == 1 && (o.near_cache < 0 ? 1 : o.near_cache));
+	         o.pack_pairs, variant == 1 && (o.near_cache < 0 ? 1 : o.near_cache),
+	         variant == 1 && (o.guard_out < 0 ? 1 : o.guard_out) && !(o.shadow_div_pretest != 0));
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

@@ -103,6 +103,7 @@ void lolb200_options_default(lolb200_options* o) {
 	o->roll_v1 = -1;
 	o->loop_worklist = -1;
 	o->near_cache = -1;
+	o->guard_out = -1;
 }
 
 /* ------------------------------------------------------- tree -> flat scene -- */

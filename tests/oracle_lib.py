@@ -203,6 +203,8 @@ static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); ret
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __saturatef(float v) { return (v > 0.f) ? ((v < 1.f) ? v : 1.f) : 0.f; }
 static inline float lol_sqrt_fast(float x) { return std::sqrt(x); }
+static inline float lol_min_nan(float a, float b) { return (a != a || b != b) ? NAN : std::fmin(a, b); }
+static inline float lol_max_nan(float a, float b) { return (a != a || b != b) ? NAN : std::fmax(a, b); }
 static inline float lol_fma(float a, float b, float c) { return std::fma(a, b, c); }
 #define __fmaf_rn lol_fma
 static inline int __float2int_rz(float f) { return (int)f; }

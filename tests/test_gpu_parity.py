@@ -391,7 +391,7 @@ def test_packed_pairs_bit_identical_to_scalar_code(name, scenes_dir):
     src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=2, pack_pairs=2))
     if name not in ("scene", "scene2"):  # their spheres are separate top-level objects: nothing to pair
         head = src.split("//@@SCENE@@")[0]
-        assert "lol_sqrt_fast2(" in head[head.index("__forceinline__ float lol_sdf("):]
+        assert "lol_sqrt_fast2(" in head[head.index("__forceinline__ float lol_sdf_try("):]
     for key in ("rgba", "id", "nprimary", "nshadow"):
         assert np.array_equal(a[key], b[key]), key
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
@@ -426,6 +426,40 @@ def test_shared_first_step_and_division_pretest_do_not_change_the_frame(name, sc
         for key in ("rgba", "id", "nprimary", "nshadow"):
             assert np.array_equal(a[key], b[key]), key
         assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
+        a["renderer"].close()
+        b["renderer"].close()
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_guard_outside_the_march_loops_does_not_change_the_frame(name, scenes_dir):
+    """guard_out (default on): variant 1's march loops run the guarded arithmetic alone (lol_sdf_try) and
+    end when the range guard fails; that march is done again from its start with the IEEE forms.
+    Against the guard's fall-back inside every evaluation (guard_out=0): the same frame, distances, ids
+    and step counts -- from the file camera, from cameras whose every ray fails the guard at step 1
+    (a sphere's centre; beyond 2^60), and from one aimed at a sphere's centre from outside (its march
+    ends at the surface; a guard can only fail where a march starts)."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    fov = scene.struct.camera.fov
+    st = scene.struct
+    centres = [list(st.nodes[i].point) for i in range(st.n_nodes) if st.nodes[i].type == 3]
+    c = centres[0] if centres else [0.0, 1.0, -6.0]
+    cams = [(None, 1920, 1080),
+            (lb.Camera.make(c, [0.2, -0.1, -1], fov), 320, 180),
+            (lb.Camera.make([3e19, 1, 0], [-1, 0, 0], fov), 160, 90),
+            (lb.Camera.make([c[0], c[1], c[2] + 64.0], [0, 0, -1], fov), 321, 181)]
+    on = lb.Options.default(variant=1, guarded_fastpath=2)
+    off = lb.Options.default(variant=1, guarded_fastpath=2, guard_out=0)
+    assert "#define LOL_GUARD_OUT 1" in lb.lower_cuda(scene, on)
+    assert "#define LOL_GUARD_OUT 0" in lb.lower_cuda(scene, off)
+    for cam, w, h in cams:
+        a = _render(lb, scene, w, h, camera=cam, options=off)
+        b = _render(lb, scene, w, h, camera=cam, options=on)
+        for key in ("rgba", "id", "nprimary", "nshadow"):
+            assert np.array_equal(a[key], b[key]), key
+        da, db = a["dist"], b["dist"]
+        assert ((da.view(np.uint32) == db.view(np.uint32)) | (np.isnan(da) & np.isnan(db))).all()
         a["renderer"].close()
         b["renderer"].close()
 

@@ -228,7 +228,8 @@ def test_box_tests_are_switched_on_where_they_pay(scenes_dir):
 
     def sdf_text(name, **kw):
         src = lb.lower_cuda(lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol")), lb.Options.default(**kw))
-        body = src[src.index("lol_sdf(const float x"):]
+        # the guarded form's arithmetic is lol_sdf_try (lol_sdf is the fall-back around it)
+        body = src[src.index("lol_sdf_try(const float x" if "lol_sdf_try(const float x" in src else "lol_sdf(const float x"):]
         return body[:body.index("//@@SCENE@@")]
 
     assert sdf_text("scene4").count("lol_box_skips(") == 1
@@ -277,7 +278,7 @@ def test_packed_pairs_structure(scenes_dir):
 
     def fast_fn(src):
         body = src.split("//@@SCENE@@")[0]
-        body = body[body.index("__forceinline__ float lol_sdf("):]
+        body = body[body.index("__forceinline__ float lol_sdf_try("):]
         # (programs with one pruned table loop carry a second form behind it: lol_sdf_slow / lol_sdf_nr)
         return body.split("// the candidate memory's way out")[0]
 
@@ -308,7 +309,7 @@ def test_packed_pairs_structure(scenes_dir):
     assert stride % 4 == 0
     # the IEEE fallback reads the same rows: a.x at slot 8, b.x next to it, a.y two further on
     ref = src.split("//@@SCENE@@")[0]
-    ref = ref[ref.index("lol_u64 lol_sdf_ref("):ref.index("__forceinline__ float lol_sdf(")]
+    ref = ref[ref.index("lol_u64 lol_sdf_ref("):ref.index("__forceinline__ float lol_sdf_try(")]
     assert "LOL_TF(c[8])" in ref and "LOL_TF(c[9])" in ref and "LOL_TF(c[10])" in ref
 
 

@@ -32,6 +32,7 @@ OPTIONS = {
     "no_skips": dict(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, share_first_step=0),
     "everything_on": dict(guarded_fastpath=2, pack_pairs=2, share_first_step=2, shadow_div_pretest=1, prune_bounds=2),
     "ieee_forms": dict(guarded_fastpath=0, prune_bounds=0),
+    "guard_inside_the_loops": dict(guard_out=0, guarded_fastpath=2),
     "forced_loops": dict(loop_threshold=2, guarded_fastpath=2, share_first_step=2),
 }
 
@@ -87,15 +88,19 @@ def test_host_compiled_pipeline_on_the_1024_sphere_scene(tmp_path):
     ("scene", (2, 2, -10), (0, 0, -1)),          # inside the round box: the march ends on step 1
     ("scene", (-0.0, 0, -0.0), (0, 0, -1)),      # -0 + rd * 0 depends on rd: the shared first step stands aside
     ("scene4", (-0.0, 6, 3), (0.3, -0.7, -1)),
+    ("scene4", (0, 1, 58), (0, 0, -1)),          # aimed at a sphere's centre from outside (the march ends at the surface: no step may fail the guard)
+    ("scene3", (np.nan, 2, 3), (0, 0, -1)),      # a NaN coordinate: min.NaN / max.NaN carry it to the guard's test
 ])
-def test_host_compiled_pipeline_edge_cameras(name, point, direction, scenes_dir, tmp_path):
+@pytest.mark.parametrize("pretest", [1, 0])     # 0: the guard outside the march loops (LOL_GUARD_OUT)
+def test_host_compiled_pipeline_edge_cameras(name, point, direction, pretest, scenes_dir, tmp_path):
     import loltracer_b200 as lb
 
     scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
     cam = lb.Camera.make(list(point), list(direction), scene.struct.camera.fov)
-    src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=2, share_first_step=2, shadow_div_pretest=1))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=2, share_first_step=2, shadow_div_pretest=pretest))
+    assert f"#define LOL_GUARD_OUT {1 - pretest}" in src
     L = ol.cpu_pipeline(tmp_path, src, "edge")
-    w, h = 64, 36
+    w, h = 65, 37  # odd: the centre pixel's ray runs along the camera direction
     _same(ol.cpu_pipeline_render(L, lb, scene, w, h, camera=cam), ol.port_render(scene, w, h, camera=cam, counts=True))
 
 
