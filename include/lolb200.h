@@ -238,14 +238,17 @@ typedef struct lolb200_options {
 	                            move before the others must be looked at again, so most
 	                            march steps evaluate the candidates and walk no group box
 	                            at all (lol_kernel.cuh: struct lol_near; exact).
-	                            1 = on, 0 = off, -1 = default (on)                   */
+	                            1 = on, 2 = on, and the warp looks at all rows again
+	                            whenever one of its lanes has to (B200, 4K: 1024 spheres
+	                            31.5 -> 29.9 ms), 0 = off, -1 = default (2)          */
 	int32_t guard_out;          /* variant 1 with the guarded forms: the march loops run the guarded
 	                            arithmetic alone and leave the loop when the range guard
 	                            fails; that one step is taken with the IEEE forms and the
 	                            loop entered again -- the fall-back call and its
 	                            reconvergence point are no longer part of every step
-	                            (exact: same evaluations, same order).
-	                            1 = on, 0 = off, -1 = default (on)                   */
+	                            (exact: same evaluations, same order).  Bits: 1 = the march
+	                            loops, 2 = the four normal taps (one test of their four
+	                            guards); 0 = off, -1 = default (3)                   */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

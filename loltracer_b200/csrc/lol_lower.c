@@ -1420,12 +1420,20 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\t\t\tbest = t%d;\n\t\t\t\tbid = oid;\n\t\t\t\twrow = row;\n\t\t\t}\n\t\t}\n"
 						          "\t\tif (round == 1)\n\t\t\tbreak;\n"
 						          "\t\t// every row outside the candidates still fails its box test here: done\n"
-						          "\t\tif (near_ok && nr.room > LOL_F(0x3f808312 /*1.004*/) * fabsf(best))\n\t\t\tbreak;\n"
+						          "\t\tconst bool need = !(near_ok && nr.room > LOL_F(0x3f808312 /*1.004*/) * fabsf(best));\n"
+						          "#if LOL_NEAR >= 2\n"
+						          "\t\t// The warp walks the rows whenever ONE of its lanes has to: the others look again too (a look is\n"
+						          "\t\t// legal at any time), which costs the warp nothing and renews their room.\n"
+						          "\t\tif (!lol_any(need))\n\t\t\tbreak;\n"
+						          "#else\n"
+						          "\t\tif (!need)\n\t\t\tbreak;\n"
+						          "#endif\n"
 						          "\t\t// look at every row again (tests only, out of line)\n"
 						          "\t\tLOL_NEAR_STAT(1, 1);\n"
 						          "\t\tconst lol_u64 seen = lol_near_collect(x, y, z, best);\n"
 						          "\t\tconst lol_u32 nc = (lol_u32)(seen & 0xffffffffull);\n"
 						          "\t\tconst float room = __uint_as_float((lol_u32)(seen >> 32));\n"
+						          "\t\tif (!need && !(room >= 0.f))\n\t\t\tbreak; // a look the ray did not need found more than four rows: what it knew still holds\n"
 						          "\t\tif (!(room >= 0.f)) { // more than four rows cannot be skipped: the plain loop, out of line\n"
 						          "\t\t\tslow = true;\n\t\t\tbreak;\n\t\t}\n"
 						          "\t\tnr.cand = nc;\n\t\tnr.room = room;\n"
@@ -1889,6 +1897,7 @@ static const char lol_near_collect_text[] =
 	"\t\t\t++nn;\n"
 	"\t\t}\n"
 	"\t}\n"
+	"\tLOL_NEAR_STAT(4 + (nn < 15u ? nn : 15u), 1);\n"
 	"\tif (nn > 4u) // an incomplete look: the low word holds the first four survivors\n"
 	"\t\troom = -1.f;\n"
 	"\telse if (!(room >= 0.f))\n"
@@ -1926,7 +1935,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
                      int prune, int two, int smem_ok, int pack, int near, int guard_out) {
 	struct sb tables = {0};
 	struct est_memo memo = {{0, 0}, {0, 0}, {NULL, NULL}};
-	near = near && prune && !two && single_pruned_run(s, loop_threshold);
+	near = (prune && !two && single_pruned_run(s, loop_threshold)) ? near : 0;
 	lol_pad_rows = near || lol_worklist;
 	sb_printf(out, "#define LOL_NEAR %d\n", near);
 	if (guarded == 1 && !guard_pays(s) && !two)
@@ -1936,7 +1945,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		int div_ok = all_divisions_provable(s);
 		sb_printf(out, "#define LOL_GUARDED 1\n#define LOL_DIV_CONST %d\n", div_ok);
 		/* variant 1's march loops call lol_sdf_try and keep the guard's fall-back outside the loop */
-		sb_printf(out, "#define LOL_GUARD_OUT %d\n", guard_out && !near && !two);
+		sb_printf(out, "#define LOL_GUARD_OUT %d\n", (!near && !two) ? guard_out : 0);
 		emit_sdf_fn(&ref, &tables, s, loop_threshold, "lol_sdf_ref", "__noinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, pack, div_ok);
 		sb_putn(out, tables.p, tables.len);
 		sb_putn(out, ref.p, ref.len);
@@ -2318,8 +2327,8 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		emit_child_materials(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
 	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */,
-	         o.pack_pairs, variant == 1 && (o.near_cache < 0 ? 1 : o.near_cache),
-	         variant == 1 && (o.guard_out < 0 ? 1 : o.guard_out) && !(o.shadow_div_pretest != 0));
+	         o.pack_pairs, variant == 1 ? (o.near_cache < 0 ? 2 : o.near_cache) : 0,
+	         (variant == 1 && !(o.shadow_div_pretest != 0)) ? (o.guard_out < 0 ? 3 : (o.guard_out & 3)) : 0);
 	sb_putn(&out, marker, strlen(marker));
 
 	if (len)

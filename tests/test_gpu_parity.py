@@ -451,7 +451,7 @@ def test_guard_outside_the_march_loops_does_not_change_the_frame(name, scenes_di
             (lb.Camera.make([c[0], c[1], c[2] + 64.0], [0, 0, -1], fov), 321, 181)]
     on = lb.Options.default(variant=1, guarded_fastpath=2)
     off = lb.Options.default(variant=1, guarded_fastpath=2, guard_out=0)
-    assert "#define LOL_GUARD_OUT 1" in lb.lower_cuda(scene, on)
+    assert "#define LOL_GUARD_OUT 3" in lb.lower_cuda(scene, on)
     assert "#define LOL_GUARD_OUT 0" in lb.lower_cuda(scene, off)
     for cam, w, h in cams:
         a = _render(lb, scene, w, h, camera=cam, options=off)
@@ -731,5 +731,11 @@ def test_candidate_memory_4k_bit_identical(name):
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
     ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
     assert {k: v for k, v in ca.items() if k != "skipped_flops"} == {k: v for k, v in cb.items() if k != "skipped_flops"}
-    a["renderer"].close()
-    b["renderer"].close()
+    # near_cache=2: the warp looks at all rows again whenever one of its lanes has to
+    c = _render(lb, scene, w, h, options=lb.Options.default(variant=1, near_cache=2, counters=1))
+    assert "#define LOL_NEAR 2" in c["renderer"].source
+    for key in ("rgba", "id", "nprimary", "nshadow"):
+        assert np.array_equal(a[key], c[key]), key
+    assert np.array_equal(a["dist"].view(np.uint32), c["dist"].view(np.uint32))
+    for r in (a, b, c):
+        r["renderer"].close()

@@ -98,7 +98,7 @@ def test_host_compiled_pipeline_edge_cameras(name, point, direction, pretest, sc
     scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
     cam = lb.Camera.make(list(point), list(direction), scene.struct.camera.fov)
     src = lb.lower_cuda(scene, lb.Options.default(variant=1, guarded_fastpath=2, share_first_step=2, shadow_div_pretest=pretest))
-    assert f"#define LOL_GUARD_OUT {1 - pretest}" in src
+    assert f"#define LOL_GUARD_OUT {3 * (1 - pretest)}" in src
     L = ol.cpu_pipeline(tmp_path, src, "edge")
     w, h = 65, 37  # odd: the centre pixel's ray runs along the camera direction
     _same(ol.cpu_pipeline_render(L, lb, scene, w, h, camera=cam), ol.port_render(scene, w, h, camera=cam, counts=True))

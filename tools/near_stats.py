@@ -17,9 +17,10 @@ with tempfile.TemporaryDirectory() as tmp:
     so = os.path.join(tmp, "p.so")
     subprocess.check_call(["g++", "-O2", "-msse4.2", "-mavx2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cu])
     L = C.CDLL(so)
-    L.lol_near_stats_ptr.restype = C.POINTER(C.c_ulonglong * 4)
+    L.lol_near_stats_ptr.restype = C.POINTER(C.c_ulonglong * 20)
     ol.cpu_pipeline_render(L, lb, scene, w, h)
     st = list(L.lol_near_stats_ptr().contents)
-calls, collects, slow, rows = st
+calls, collects, slow, rows = st[:4]
 print(f"{name} {w}x{h}: {calls} sdf calls, rows looked at again in {collects / calls:.1%} of them, the long way in "
       f"{slow / calls:.1%}, {rows / calls:.2f} rows evaluated per call (+ the long way's)")
+print("rows that could not be skipped per look:", " ".join(f"{n}:{v / max(collects, 1):.1%}" for n, v in enumerate(st[4:])))
