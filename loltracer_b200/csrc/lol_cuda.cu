@@ -91,6 +91,7 @@ struct lolb200_renderer {
 	int threads = LOLB200_KERNEL_THREADS; /* CTA size the program was generated for */
 	size_t dyn_smem = 0; /* variant 2: warp-private queues */
 	cudaKernel_t resume_kernel = nullptr; /* variant 4: lol_resume */
+	bool long_sdf = false;                /* the program uses the guarded forms (pick_chunk_w) */
 	lol_u32* queue[LOL_MAX_SLABS] = {};    /* variant 4: continuation queues of each work-counter slot */
 	size_t queue_slots[LOL_MAX_SLABS] = {}; /* records per queue (one queue per class: 1 + lights) */
 	int queue_classes = 0;
@@ -553,8 +554,19 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 		CREATE_TRY(cudaMalloc(&r->queue_ctl, 64 * LOL_MAX_SLABS * sizeof(lol_u32)));
 		CREATE_TRY(cudaMemset(r->queue_ctl, 0, 64 * LOL_MAX_SLABS * sizeof(lol_u32)));
 	}
+	if (strstr(r->source.c_str(), "extern \"C\" __global__ void lol_grid_build()") &&
+	    !strstr(r->source.c_str(), "#define LOL_NEAR_GRID (0 &&") && !strstr(r->source.c_str(), "#define LOL_GRID_OK 0")) {
+		/* the candidate grid of a pruned table loop (lol_lower.c: lol_near_grid_text): one thread per cell, once */
+		cudaKernel_t build = nullptr;
+		CREATE_TRY(cudaLibraryGetKernel(&build, r->lib, "lol_grid_build"));
+		const char* gn = strstr(r->source.c_str(), "#define LOL_GRID_N ");
+		const int n = gn ? atoi(gn + strlen("#define LOL_GRID_N ")) : 32;
+		CREATE_TRY(cudaLaunchKernel((const void*)build, dim3((unsigned)((n * n * n + 127) / 128)), dim3(128), nullptr, 0, nullptr));
+		CREATE_TRY(cudaDeviceSynchronize());
+	}
 	{
 		/* the lowering states what it generated */
+		r->long_sdf = strstr(r->source.c_str(), "#define LOL_GUARDED 1") != nullptr;
 		const char* v = strstr(r->source.c_str(), "#define LOL_VARIANT ");
 		r->variant = v ? atoi(v + strlen("#define LOL_VARIANT ")) : 1;
 		const char* th = strstr(r->source.c_str(), "#define LOL_THREADS ");
@@ -660,9 +672,21 @@ static lol_u32 pick_chunk_w(const lolb200_renderer* r, int w, size_t local_bands
 	const size_t warps = (size_t)r->sm_count * r->blocks_per_sm * (r->threads / 32);
 	/* variant 3: a warp step covers 16 x 4 pixels (two per lane) */
 	const lol_u32 min_w = r->variant == 3 ? 16 : 8;
+	static const int forced = [] { /* LOLB200_CHUNK_W=<8|16|32|64> forces a width (A/B) */
+		const char* e = getenv("LOLB200_CHUNK_W");
+		return e ? atoi(e) : 0;
+	}();
+	if (forced >= (int)min_w && forced <= 64 && (forced & (forced - 1)) == 0)
+		return (lol_u32)forced;
+	/* A chunk is marched by ONE warp, tile after tile, and the frame cannot end before its longest chunk
+	 * does.  Programs with the guarded forms are the ones with long distance functions (>= 3 spheres or a
+	 * smooth union): they get twice as many, half as wide chunks.  Measured on B200 at 4K (chunks of 8 against
+	 * 16 pixels): scene4 2.027 -> 1.999 ms (tail 63 -> 6 us), scene2 0.989 -> 0.976, scene3 0.881 -> 0.868;
+	 * scene.lol (no guard, short marches) 0.644 -> 0.660: it keeps the wide ones. */
+	const size_t per_warp = r->long_sdf ? 32 : 16;
 	for (lol_u32 cw = r->variant == 2 ? 32 : 64; cw > min_w; cw >>= 1) {
 		size_t chunks = (((size_t)w + cw - 1) / cw) * local_bands;
-		if (chunks >= 16 * warps)
+		if (chunks >= per_warp * warps)
 			return cw;
 	}
 	return min_w;
@@ -754,6 +778,17 @@ static void lpt_after_launch(lolb200_renderer* r, void* stream) {
 		cub::DeviceRadixSort::SortPairsDescending(L.tmp, tmp_bytes, L.cost, L.cost_sorted, L.ids, L.order,
 		                                          (int)L.n_chunks, 0, 32, (cudaStream_t)stream);
 		L.have_order = true;
+		/* debugging aid: LOLB200_LPT_DUMP=<file> writes the chunk costs (clocks, u32 each) of the 16th frame */
+		if (f == 15)
+			if (const char* path = getenv("LOLB200_LPT_DUMP")) {
+				std::vector<lol_u32> host(L.n_chunks);
+				cudaStreamSynchronize((cudaStream_t)stream);
+				cudaMemcpy(host.data(), L.cost, host.size() * sizeof(lol_u32), cudaMemcpyDeviceToHost);
+				if (FILE* fp = fopen(path, "wb")) {
+					fwrite(host.data(), sizeof(lol_u32), host.size(), fp);
+					fclose(fp);
+				}
+			}
 	}
 }
 

@@ -1048,7 +1048,7 @@ static void tab_start(struct tabs* T, const char* fmt, int run_no) {
 		T->n++;
 	}
 	snprintf(name, sizeof name, fmt, run_no);
-	sb_printf(&T->defs, "#define %s (LOL_TAB + %zu)\n", name, T->n);
+	sb_printf(&T->defs, "#define %s (LOL_TAB + %zu)\n#define %s_offset %zuu\n", name, T->n, name, T->n);
 	sb_printf(&T->words, "\n\t/* %s */\n", name);
 }
 
@@ -1650,6 +1650,29 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				}
 				sb_printf(&tables.defs, "#define LOL_RUN%d_STRIDE %zu\n#define LOL_RUN%d_ROWS %u\n#define LOL_RUN%d_GROUP %u\n",
 				          run_no, per_row, run_no, n, run_no, LOL_GROUP);
+				if (run_no == 0) {
+					/* the domain of the candidate grid (lol_near_collect_text): the box around every row's box, a
+					 * tenth of its size wider on every side, cut into LOL_GRID_N^3 cells */
+					float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
+					int ok = 1;
+					for (uint32_t k = 0; k < n; k++)
+						for (int a = 0; a < 3; a++) {
+							ok &= isfinite(boxes[k][a]) && isfinite(boxes[k][3 + a]) && isfinite(boxes[k][6]);
+							lo3[a] = fminf(lo3[a], boxes[k][a] - boxes[k][3 + a] - boxes[k][6]);
+							hi3[a] = fmaxf(hi3[a], boxes[k][a] + boxes[k][3 + a] + boxes[k][6]);
+						}
+					sb_printf(&tables.defs, "#define LOL_GRID_OK %d\n#define LOL_GRID_N 32\n", ok);
+					for (int a = 0; a < 3 && ok; a++) {
+						const float size = (hi3[a] - lo3[a]) * 1.2f + 1e-3f, x0 = lo3[a] - (hi3[a] - lo3[a]) * 0.1f - 5e-4f;
+						sb_printf(&tables.defs, "#define LOL_GRID_%c0 ", "XYZ"[a]);
+						sb_float(&tables.defs, x0);
+						sb_printf(&tables.defs, "\n#define LOL_GRID_S%c ", "XYZ"[a]);
+						sb_float(&tables.defs, size / 32.f);
+						sb_printf(&tables.defs, "\n#define LOL_GRID_I%c ", "XYZ"[a]);
+						sb_float(&tables.defs, 32.f / size);
+						sb_printf(&tables.defs, "\n");
+					}
+				}
 				run_no++;
 				free(boxes);
 				free(order);
@@ -1867,6 +1890,67 @@ static const char lol_sdf_slow_text[] =
 	"\tlol_u32 id;\n\tconst float d = lol_sdf(x, y, z, hint, id);\n"
 	"\treturn ((lol_u64)id << 32) | (lol_u64)__float_as_uint(d);\n}\n";
 
+/* The candidate grid of LOL_NEAR programs (options.near_cache = 3).  Looking at every row again -- 16 group tests
+ * and the member tests of the groups that survive -- is a third of what the 1024-primitive scenes execute.  Which
+ * rows can matter at a point is mostly a matter of WHERE the point is, and the scene does not move: the box around
+ * all rows is cut into LOL_GRID_N^3 cells, and every cell knows the eight rows nearest to it, sorted by a lower
+ * bound w of  dbox_row(p) - m1_row  over every point p of the cell (distance between the two boxes), and the bound
+ * of the ninth.  A look then reads its cell: the rows with w <= 1.004 |best| are the only ones that can fail to be
+ * skipped (their own box test decides, as before); the first w above it is the room.  A list that ends before
+ * such a w is found (a crowd, or a large `best`), or a point outside the grid: every row is looked at, as before.
+ * The grid is built on the device by lol_grid_build (one thread per cell, once per renderer) from the same table
+ * the loops read; the bounds are lowered by 0.01 % and LOL_NEAR_PAD, the cells widened by 0.1 %. */
+static const char lol_near_grid_text[] =
+	"#if LOL_NEAR_GRID\n"
+	"struct __align__(16) lol_cell {\n"
+	"\tfloat w[8];       // lower bounds of dbox(p) - m1 over the cell, ascending (+INF: no row)\n"
+	"\tlol_u32 rows[2];  // their rows, one per byte\n"
+	"\tfloat rest;       // the bound of every row that is not listed\n"
+	"\tlol_u32 pad;\n"
+	"};\n"
+	"#ifdef LOL_HOST_SHIM\n"
+	"static lol_cell lol_grid[LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
+	"#else\n"
+	"__device__ lol_cell lol_grid[LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
+	"#endif\n"
+	"__device__ void lol_grid_build_cell(const int ci) {\n"
+	"\tconst int ix = ci % LOL_GRID_N, iy = (ci / LOL_GRID_N) % LOL_GRID_N, iz = ci / (LOL_GRID_N * LOL_GRID_N);\n"
+	"\tconst float cx = LOL_GRID_X0 + ((float)ix + .5f) * LOL_GRID_SX, cy = LOL_GRID_Y0 + ((float)iy + .5f) * LOL_GRID_SY,\n"
+	"\t            cz = LOL_GRID_Z0 + ((float)iz + .5f) * LOL_GRID_SZ;\n"
+	"\tconst float hx = .5005f * LOL_GRID_SX + LOL_NEAR_PAD, hy = .5005f * LOL_GRID_SY + LOL_NEAR_PAD,\n"
+	"\t            hz = .5005f * LOL_GRID_SZ + LOL_NEAR_PAD;\n"
+	"\tfloat w[9];\n"
+	"\tlol_u32 r[9];\n"
+	"\tfor (int k = 0; k < 9; ++k) {\n\t\tw[k] = LOL_INF;\n\t\tr[k] = 0xffu;\n\t}\n"
+	"\tfor (int i = 0; i < LOL_RUN0_ROWS; ++i) {\n"
+	"\t\tconst lol_u32* ct = lol_tables + lol_run0_offset + i * LOL_RUN0_STRIDE;\n"
+	"\t\tconst float gx = fmaxf(fabsf(cx - LOL_TF(ct[0])) - (hx + LOL_TF(ct[3])), 0.f);\n"
+	"\t\tconst float gy = fmaxf(fabsf(cy - LOL_TF(ct[1])) - (hy + LOL_TF(ct[4])), 0.f);\n"
+	"\t\tconst float gz = fmaxf(fabsf(cz - LOL_TF(ct[2])) - (hz + LOL_TF(ct[5])), 0.f);\n"
+	"\t\tfloat v = sqrtf(gx * gx + gy * gy + gz * gz) * 0.9999f - LOL_TF(ct[6]) - LOL_NEAR_PAD;\n"
+	"\t\tlol_u32 vr = (lol_u32)i;\n"
+	"\t\tfor (int k = 0; k < 9; ++k) // insertion into the nine smallest\n"
+	"\t\t\tif (v < w[k]) {\n"
+	"\t\t\t\tconst float tw = w[k];\n\t\t\t\tconst lol_u32 tr = r[k];\n"
+	"\t\t\t\tw[k] = v;\n\t\t\t\tr[k] = vr;\n\t\t\t\tv = tw;\n\t\t\t\tvr = tr;\n"
+	"\t\t\t}\n"
+	"\t}\n"
+	"\tlol_cell c;\n"
+	"\tfor (int k = 0; k < 8; ++k)\n\t\tc.w[k] = w[k];\n"
+	"\tc.rows[0] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);\n"
+	"\tc.rows[1] = r[4] | (r[5] << 8) | (r[6] << 16) | (r[7] << 24);\n"
+	"\tc.rest = w[8];\n"
+	"\tc.pad = 0u;\n"
+	"\tlol_grid[ci] = c;\n"
+	"}\n"
+	"#ifndef LOL_HOST_SHIM\n"
+	"extern \"C\" __global__ void lol_grid_build() {\n"
+	"\tconst int ci = (int)(blockIdx.x * blockDim.x + threadIdx.x);\n"
+	"\tif (ci < LOL_GRID_N * LOL_GRID_N * LOL_GRID_N)\n\t\tlol_grid_build_cell(ci);\n"
+	"}\n"
+	"#endif\n"
+	"#endif // LOL_NEAR_GRID\n";
+
 static const char lol_near_collect_text[] =
 	"// Every row of the pruned table loop against `best`, tests only (lol_kernel.cuh: struct lol_near): the rows\n"
 	"// that cannot be skipped (the first four, one per byte of the low word) and, in the high word, a lower bound of\n"
@@ -1875,6 +1959,44 @@ static const char lol_near_collect_text[] =
 	"__device__ __noinline__ lol_u64 lol_near_collect(const float x, const float y, const float z, const float best) {\n"
 	"\tfloat room = LOL_INF;\n"
 	"\tlol_u32 nc = 0xffffffffu, nn = 0u;\n"
+	"#if LOL_NEAR_GRID\n"
+	"\t{ // the point's cell knows the rows that can matter here, nearest first (lol_grid_build_cell)\n"
+	"\t\tconst float fx = (x - LOL_GRID_X0) * LOL_GRID_IX, fy = (y - LOL_GRID_Y0) * LOL_GRID_IY, fz = (z - LOL_GRID_Z0) * LOL_GRID_IZ;\n"
+	"\t\tconst float top = (float)LOL_GRID_N;\n"
+	"\t\tif (fx >= 0.f && fx < top && fy >= 0.f && fy < top && fz >= 0.f && fz < top) { // (a NaN is outside)\n"
+	"\t\t\tconst lol_cell cell = lol_grid[((int)fz * LOL_GRID_N + (int)fy) * LOL_GRID_N + (int)fx];\n"
+	"\t\t\tconst float thr = fabsf(best) * LOL_F(0x3f808366 /*1.00401*/); // a row with w > 1.004 |best| is skipped wherever the point is in the cell\n"
+	"\t\t\tfloat next = cell.rest;\n"
+	"\t\t\tint c = 0;\n"
+	"#pragma unroll\n"
+	"\t\t\tfor (int k = 7; k >= 0; --k) {\n"
+	"\t\t\t\tif (cell.w[k] > thr)\n\t\t\t\t\tnext = cell.w[k];\n\t\t\t\telse\n\t\t\t\t\t++c;\n"
+	"\t\t\t}\n"
+	"\t\t\tif (next > thr) { // the list is complete for this `best`: its first c rows, and `next` bounds all others\n"
+	"\t\t\t\tLOL_NEAR_STAT(20, 1);\n"
+	"\t\t\t\troom = next;\n"
+	"\t\t\t\tconst lol_u64 rows = (lol_u64)cell.rows[0] | ((lol_u64)cell.rows[1] << 32);\n"
+	"#pragma unroll 1\n"
+	"\t\t\t\tfor (int k = 0; k < c; ++k) {\n"
+	"\t\t\t\t\tconst lol_u32 i = (lol_u32)(rows >> (8 * k)) & 0xffu;\n"
+	"\t\t\t\t\tconst lol_u32* ct = lol_run0 + i * LOL_RUN0_STRIDE;\n"
+	"\t\t\t\t\tconst float q2 = lol_box_q2(x, y, z, LOL_TF(ct[0]), LOL_TF(ct[1]), LOL_TF(ct[2]), LOL_TF(ct[3]), LOL_TF(ct[4]), LOL_TF(ct[5]));\n"
+	"\t\t\t\t\tif (lol_q2_skips(q2, LOL_TF(ct[6]), best)) {\n"
+	"\t\t\t\t\t\troom = fminf(room, lol_box_gap(q2, LOL_TF(ct[6])));\n"
+	"\t\t\t\t\t\tcontinue;\n"
+	"\t\t\t\t\t}\n"
+	"\t\t\t\t\tif (nn < 4u)\n"
+	"\t\t\t\t\t\tnc = (nc & ~(0xffu << (8u * nn))) | (i << (8u * nn));\n"
+	"\t\t\t\t\t++nn;\n"
+	"\t\t\t\t}\n"
+	"\t\t\t\tLOL_NEAR_STAT(4 + (nn < 15u ? nn : 15u), 1);\n"
+	"\t\t\t\tif (nn > 4u)\n\t\t\t\t\troom = -1.f;\n"
+	"\t\t\t\telse if (!(room >= 0.f))\n\t\t\t\t\troom = 0.f;\n"
+	"\t\t\t\treturn (lol_u64)nc | ((lol_u64)__float_as_uint(room) << 32);\n"
+	"\t\t\t}\n"
+	"\t\t}\n"
+	"\t}\n"
+	"#endif\n"
 	"#pragma unroll 1\n"
 	"\tfor (int g = 0; g * LOL_RUN0_GROUP < LOL_RUN0_ROWS; ++g) {\n"
 	"\t\tconst lol_u32* gc = lol_run0_groups + g * 7;\n"
@@ -1937,7 +2059,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 	struct est_memo memo = {{0, 0}, {0, 0}, {NULL, NULL}};
 	near = (prune && !two && single_pruned_run(s, loop_threshold)) ? near : 0;
 	lol_pad_rows = near || lol_worklist;
-	sb_printf(out, "#define LOL_NEAR %d\n", near);
+	sb_printf(out, "#define LOL_NEAR %d\n", near > 2 ? 2 : near);
 	if (guarded == 1 && !guard_pays(s) && !two)
 		guarded = 0;
 	if (guarded && constants_in_range(s)) {
@@ -1956,6 +2078,8 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 			            "lol_sdf_ref", prune, 1, smem_ok, &memo, 0, pack, div_ok);
 		if (near) {
 			sb_printf(out, "%s", lol_sdf_slow_text);
+			sb_printf(out, "#define LOL_NEAR_GRID (%d && LOL_GRID_OK)\n", near >= 3);
+			sb_putn(out, lol_near_grid_text, strlen(lol_near_grid_text));
 			sb_putn(out, lol_near_collect_text, strlen(lol_near_collect_text));
 			lol_emit_near = 1;
 			sb_printf(out, "#define lol_pairc lol_pairc_nr // this form's own pair constants\n");
@@ -1974,6 +2098,8 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		free(fn.p);
 		if (near) {
 			sb_printf(out, "%s", lol_sdf_slow_text);
+			sb_printf(out, "#define LOL_NEAR_GRID (%d && LOL_GRID_OK)\n", near >= 3);
+			sb_putn(out, lol_near_grid_text, strlen(lol_near_grid_text));
 			sb_putn(out, lol_near_collect_text, strlen(lol_near_collect_text));
 			lol_emit_near = 1;
 			emit_sdf_fn(out, NULL, s, loop_threshold, "lol_sdf_nr", "__forceinline__", 0, 0, NULL, prune, 0, smem_ok, &memo, 0, 0, 0);

@@ -281,15 +281,21 @@ def test_candidate_memory_of_pruned_loops_is_exact(kind, tmp_path):
     want = ol.port_render(scene, w, h, counts=True)
     for tag, kw in (("on", dict(near_cache=1)), ("off", dict(near_cache=0)),
                     ("ieee", dict(near_cache=1, guarded_fastpath=0, pack_pairs=0)),
-                    ("noskip", dict(near_cache=1, skip_black_miss=0, cull_backfacing=0, shadow_early_out=0))):
+                    ("noskip", dict(near_cache=1, skip_black_miss=0, cull_backfacing=0, shadow_early_out=0)),
+                    # 3: looks are answered by the candidate grid (every cell knows its eight nearest rows)
+                    ("grid", dict(near_cache=3)),
+                    ("grid_ieee_noskip", dict(near_cache=3, guarded_fastpath=0, pack_pairs=0, skip_black_miss=0,
+                                              cull_backfacing=0, shadow_early_out=0))):
         src = lb.lower_cuda(scene, lb.Options.default(variant=1, loop_threshold=8, **kw))
-        assert f"#define LOL_NEAR {int(kw['near_cache'])}" in src
+        assert f"#define LOL_NEAR {min(int(kw['near_cache']), 2)}" in src
+        assert ("#define LOL_NEAR_GRID (1 &&" in src) == (kw["near_cache"] == 3)
         L = ol.cpu_pipeline(tmp_path, src, f"near_{kind}_{tag}")
         _same(ol.cpu_pipeline_render(L, lb, scene, w, h), want, shadow_counts=(tag == "noskip"))
     # cameras inside the crowd, far away (beyond the coordinate range the memory trusts) and NaN
     cams = [lb.Camera.make([0, 1, -5.5], [0.2, -0.1, -1], 1.5), lb.Camera.make([0, 2, 900], [0, 0, -1], 0.3),
             lb.Camera.make([0, 5, -6], [0, -1, 0], 1.5)]
-    src = lb.lower_cuda(scene, lb.Options.default(variant=1, loop_threshold=8, near_cache=1))
-    L = ol.cpu_pipeline(tmp_path, src, f"near_{kind}_cams")
-    for cam in cams:
-        _same(ol.cpu_pipeline_render(L, lb, scene, 48, 27, camera=cam), ol.port_render(scene, 48, 27, camera=cam, counts=True))
+    for near in (1, 3):
+        src = lb.lower_cuda(scene, lb.Options.default(variant=1, loop_threshold=8, near_cache=near))
+        L = ol.cpu_pipeline(tmp_path, src, f"near_{kind}_cams{near}")
+        for cam in cams:
+            _same(ol.cpu_pipeline_render(L, lb, scene, 48, 27, camera=cam), ol.port_render(scene, 48, 27, camera=cam, counts=True))
