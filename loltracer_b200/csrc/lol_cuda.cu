@@ -561,7 +561,7 @@ extern "C" int lolb200_renderer_create(const lolb200_scene* s, const lolb200_opt
 		CREATE_TRY(cudaLibraryGetKernel(&build, r->lib, "lol_grid_build"));
 		const char* gn = strstr(r->source.c_str(), "#define LOL_GRID_N ");
 		const int n = gn ? atoi(gn + strlen("#define LOL_GRID_N ")) : 32;
-		CREATE_TRY(cudaLaunchKernel((const void*)build, dim3((unsigned)((n * n * n + 127) / 128)), dim3(128), nullptr, 0, nullptr));
+		CREATE_TRY(cudaLaunchKernel((const void*)build, dim3((unsigned)((2 * n * n * n + 127) / 128)), dim3(128), nullptr, 0, nullptr));
 		CREATE_TRY(cudaDeviceSynchronize());
 	}
 	{

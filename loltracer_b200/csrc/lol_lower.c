@@ -98,6 +98,8 @@ struct pairc { /* the constant pairs of one function: (low, high) bits */
 	uint32_t (*w)[2];
 	size_t n, cap;
 };
+#define LOL_GRID_OUTER_F 4.f /* the outer candidate grid's cells are this many times as large (lol_near_grid_text) */
+
 struct cgen {
 	const lolb200_scene* s;
 	struct sb* out;
@@ -1661,7 +1663,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 							lo3[a] = fminf(lo3[a], boxes[k][a] - boxes[k][3 + a] - boxes[k][6]);
 							hi3[a] = fmaxf(hi3[a], boxes[k][a] + boxes[k][3 + a] + boxes[k][6]);
 						}
-					sb_printf(&tables.defs, "#define LOL_GRID_OK %d\n#define LOL_GRID_N 32\n", ok);
+					sb_printf(&tables.defs, "#define LOL_GRID_OK %d\n#define LOL_GRID_N 32\n#define LOL_GRID_OUTER %.1ff\n", ok, LOL_GRID_OUTER_F);
 					for (int a = 0; a < 3 && ok; a++) {
 						const float size = (hi3[a] - lo3[a]) * 1.2f + 1e-3f, x0 = lo3[a] - (hi3[a] - lo3[a]) * 0.1f - 5e-4f;
 						sb_printf(&tables.defs, "#define LOL_GRID_%c0 ", "XYZ"[a]);
@@ -1670,6 +1672,9 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						sb_float(&tables.defs, size / 32.f);
 						sb_printf(&tables.defs, "\n#define LOL_GRID_I%c ", "XYZ"[a]);
 						sb_float(&tables.defs, 32.f / size);
+						/* the outer grid: cells LOL_GRID_OUTER times as large, around the same centre */
+						sb_printf(&tables.defs, "\n#define LOL_GRID_%c1 ", "XYZ"[a]);
+						sb_float(&tables.defs, x0 - size * (0.5f * (LOL_GRID_OUTER_F - 1.f)));
 						sb_printf(&tables.defs, "\n");
 					}
 				}
@@ -1909,16 +1914,20 @@ static const char lol_near_grid_text[] =
 	"\tlol_u32 pad;\n"
 	"};\n"
 	"#ifdef LOL_HOST_SHIM\n"
-	"static lol_cell lol_grid[LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
+	"static lol_cell lol_grid[2 * LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
 	"#else\n"
-	"__device__ lol_cell lol_grid[LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
+	"__device__ lol_cell lol_grid[2 * LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
 	"#endif\n"
-	"__device__ void lol_grid_build_cell(const int ci) {\n"
+	"// level 0: the fine grid around the rows; level 1: the same number of cells, LOL_GRID_OUTER times as large each,\n"
+	"// around the same centre -- for the points of rays on their way in and out\n"
+	"__device__ void lol_grid_build_cell(const int cell) {\n"
+	"\tconst int level = cell / (LOL_GRID_N * LOL_GRID_N * LOL_GRID_N), ci = cell % (LOL_GRID_N * LOL_GRID_N * LOL_GRID_N);\n"
 	"\tconst int ix = ci % LOL_GRID_N, iy = (ci / LOL_GRID_N) % LOL_GRID_N, iz = ci / (LOL_GRID_N * LOL_GRID_N);\n"
-	"\tconst float cx = LOL_GRID_X0 + ((float)ix + .5f) * LOL_GRID_SX, cy = LOL_GRID_Y0 + ((float)iy + .5f) * LOL_GRID_SY,\n"
-	"\t            cz = LOL_GRID_Z0 + ((float)iz + .5f) * LOL_GRID_SZ;\n"
-	"\tconst float hx = .5005f * LOL_GRID_SX + LOL_NEAR_PAD, hy = .5005f * LOL_GRID_SY + LOL_NEAR_PAD,\n"
-	"\t            hz = .5005f * LOL_GRID_SZ + LOL_NEAR_PAD;\n"
+	"\tconst float sx = level ? LOL_GRID_SX * LOL_GRID_OUTER : LOL_GRID_SX, sy = level ? LOL_GRID_SY * LOL_GRID_OUTER : LOL_GRID_SY,\n"
+	"\t            sz = level ? LOL_GRID_SZ * LOL_GRID_OUTER : LOL_GRID_SZ;\n"
+	"\tconst float x0 = level ? LOL_GRID_X1 : LOL_GRID_X0, y0 = level ? LOL_GRID_Y1 : LOL_GRID_Y0, z0 = level ? LOL_GRID_Z1 : LOL_GRID_Z0;\n"
+	"\tconst float cx = x0 + ((float)ix + .5f) * sx, cy = y0 + ((float)iy + .5f) * sy, cz = z0 + ((float)iz + .5f) * sz;\n"
+	"\tconst float hx = .5005f * sx + LOL_NEAR_PAD, hy = .5005f * sy + LOL_NEAR_PAD, hz = .5005f * sz + LOL_NEAR_PAD;\n"
 	"\tfloat w[9];\n"
 	"\tlol_u32 r[9];\n"
 	"\tfor (int k = 0; k < 9; ++k) {\n\t\tw[k] = LOL_INF;\n\t\tr[k] = 0xffu;\n\t}\n"
@@ -1941,12 +1950,12 @@ static const char lol_near_grid_text[] =
 	"\tc.rows[1] = r[4] | (r[5] << 8) | (r[6] << 16) | (r[7] << 24);\n"
 	"\tc.rest = w[8];\n"
 	"\tc.pad = 0u;\n"
-	"\tlol_grid[ci] = c;\n"
+	"\tlol_grid[cell] = c;\n"
 	"}\n"
 	"#ifndef LOL_HOST_SHIM\n"
 	"extern \"C\" __global__ void lol_grid_build() {\n"
 	"\tconst int ci = (int)(blockIdx.x * blockDim.x + threadIdx.x);\n"
-	"\tif (ci < LOL_GRID_N * LOL_GRID_N * LOL_GRID_N)\n\t\tlol_grid_build_cell(ci);\n"
+	"\tif (ci < 2 * LOL_GRID_N * LOL_GRID_N * LOL_GRID_N)\n\t\tlol_grid_build_cell(ci);\n"
 	"}\n"
 	"#endif\n"
 	"#endif // LOL_NEAR_GRID\n";
@@ -1961,10 +1970,17 @@ static const char lol_near_collect_text[] =
 	"\tlol_u32 nc = 0xffffffffu, nn = 0u;\n"
 	"#if LOL_NEAR_GRID\n"
 	"\t{ // the point's cell knows the rows that can matter here, nearest first (lol_grid_build_cell)\n"
-	"\t\tconst float fx = (x - LOL_GRID_X0) * LOL_GRID_IX, fy = (y - LOL_GRID_Y0) * LOL_GRID_IY, fz = (z - LOL_GRID_Z0) * LOL_GRID_IZ;\n"
+	"\t\tfloat fx = (x - LOL_GRID_X0) * LOL_GRID_IX, fy = (y - LOL_GRID_Y0) * LOL_GRID_IY, fz = (z - LOL_GRID_Z0) * LOL_GRID_IZ;\n"
 	"\t\tconst float top = (float)LOL_GRID_N;\n"
+	"\t\tint base = 0;\n"
+	"\t\tif (!(fx >= 0.f && fx < top && fy >= 0.f && fy < top && fz >= 0.f && fz < top)) { // not in the fine grid: the outer one\n"
+	"\t\t\tfx = (x - LOL_GRID_X1) * (LOL_GRID_IX / LOL_GRID_OUTER);\n"
+	"\t\t\tfy = (y - LOL_GRID_Y1) * (LOL_GRID_IY / LOL_GRID_OUTER);\n"
+	"\t\t\tfz = (z - LOL_GRID_Z1) * (LOL_GRID_IZ / LOL_GRID_OUTER);\n"
+	"\t\t\tbase = LOL_GRID_N * LOL_GRID_N * LOL_GRID_N;\n"
+	"\t\t}\n"
 	"\t\tif (fx >= 0.f && fx < top && fy >= 0.f && fy < top && fz >= 0.f && fz < top) { // (a NaN is outside)\n"
-	"\t\t\tconst lol_cell cell = lol_grid[((int)fz * LOL_GRID_N + (int)fy) * LOL_GRID_N + (int)fx];\n"
+	"\t\t\tconst lol_cell cell = lol_grid[base + ((int)fz * LOL_GRID_N + (int)fy) * LOL_GRID_N + (int)fx];\n"
 	"\t\t\tconst float thr = fabsf(best) * LOL_F(0x3f808366 /*1.00401*/); // a row with w > 1.004 |best| is skipped wherever the point is in the cell\n"
 	"\t\t\tfloat next = cell.rest;\n"
 	"\t\t\tint c = 0;\n"
@@ -1994,7 +2010,9 @@ static const char lol_near_collect_text[] =
 	"\t\t\t\telse if (!(room >= 0.f))\n\t\t\t\t\troom = 0.f;\n"
 	"\t\t\t\treturn (lol_u64)nc | ((lol_u64)__float_as_uint(room) << 32);\n"
 	"\t\t\t}\n"
-	"\t\t}\n"
+	"\t\t\tLOL_NEAR_STAT(22, 1); // the cell's list ends before a bound above the threshold\n"
+	"\t\t} else\n"
+	"\t\t\tLOL_NEAR_STAT(21, 1); // outside the grid\n"
 	"\t}\n"
 	"#endif\n"
 	"#pragma unroll 1\n"

@@ -731,11 +731,25 @@ def test_candidate_memory_4k_bit_identical(name):
     assert np.array_equal(a["dist"].view(np.uint32), b["dist"].view(np.uint32))
     ca, cb = a["renderer"].read_counters(), b["renderer"].read_counters()
     assert {k: v for k, v in ca.items() if k != "skipped_flops"} == {k: v for k, v in cb.items() if k != "skipped_flops"}
-    # near_cache=2: the warp looks at all rows again whenever one of its lanes has to
-    c = _render(lb, scene, w, h, options=lb.Options.default(variant=1, near_cache=2, counters=1))
-    assert "#define LOL_NEAR 2" in c["renderer"].source
-    for key in ("rgba", "id", "nprimary", "nshadow"):
-        assert np.array_equal(a[key], c[key]), key
-    assert np.array_equal(a["dist"].view(np.uint32), c["dist"].view(np.uint32))
-    for r in (a, b, c):
+    # near_cache=2: the warp looks at all rows again whenever one of its lanes has to;
+    # near_cache=3: and a look reads the point's cell of the candidate grid (built on the device at creation)
+    for near in (2, 3):
+        c = _render(lb, scene, w, h, options=lb.Options.default(variant=1, near_cache=near, counters=1))
+        assert "#define LOL_NEAR 2" in c["renderer"].source
+        assert ("#define LOL_NEAR_GRID (1 &&" in c["renderer"].source) == (near == 3)
+        for key in ("rgba", "id", "nprimary", "nshadow"):
+            assert np.array_equal(a[key], c[key]), (near, key)
+        assert np.array_equal(a["dist"].view(np.uint32), c["dist"].view(np.uint32))
+        c["renderer"].close()
+    # the grid from cameras inside the crowd and far outside the grid's domain
+    for point, direction in (((0.3, 2.8, -9.0), (0.2, -0.1, -1.0)), ((60.0, 30.0, 40.0), (-0.6, -0.3, -0.7))):
+        cam = lb.Camera.make(list(point), list(direction), scene.struct.camera.fov)
+        p = _render(lb, scene, 1280, 720, camera=cam, options=lb.Options.default(variant=1, near_cache=0))
+        q = _render(lb, scene, 1280, 720, camera=cam, options=lb.Options.default(variant=1, near_cache=3))
+        for key in ("rgba", "id", "nprimary", "nshadow"):
+            assert np.array_equal(p[key], q[key]), (point, key)
+        assert np.array_equal(p["dist"].view(np.uint32), q["dist"].view(np.uint32))
+        p["renderer"].close()
+        q["renderer"].close()
+    for r in (a, b):
         r["renderer"].close()

@@ -25,4 +25,5 @@ calls, collects, slow, rows = st[:4]
 print(f"{name} {w}x{h}: {calls} sdf calls, rows looked at again in {collects / calls:.1%} of them, the long way in "
       f"{slow / calls:.1%}, {rows / calls:.2f} rows evaluated per call (+ the long way's)")
 print("rows that could not be skipped per look:", " ".join(f"{n}:{v / max(collects, 1):.1%}" for n, v in enumerate(st[4:20])))
-print(f"looks answered by the candidate grid: {st[20] / max(collects, 1):.1%}")
+print(f"looks answered by the candidate grid: {st[20] / max(collects, 1):.1%}; point outside the grid: {st[21] / max(collects, 1):.1%}; "
+      f"the cell's list too short: {st[22] / max(collects, 1):.1%}")
