@@ -240,7 +240,12 @@ typedef struct lolb200_options {
 	                            at all (lol_kernel.cuh: struct lol_near; exact).
 	                            1 = on, 2 = on, and the warp looks at all rows again
 	                            whenever one of its lanes has to (B200, 4K: 1024 spheres
-	                            31.5 -> 29.9 ms), 0 = off, -1 = default (2)          */
+	                            31.5 -> 29.9 ms), 3 = and a look reads the point's cell
+	                            of a candidate grid (two levels of 32^3 cells, each with
+	                            its eight nearest rows, built on the device when the
+	                            renderer is created) instead of walking every group,
+	                            and up to eight rows are evaluated on the spot before
+	                            the plain loop is called in, 0 = off, -1 = default (3) */
 	int32_t guard_out;          /* variant 1 with the guarded forms: the march loops run the guarded
 	                            arithmetic alone and leave the loop when the range guard
 	                            fails; that one step is taken with the IEEE forms and the

@@ -1389,20 +1389,21 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\tnr.room -= lol_fma(move, LOL_F(0x3f800347 /*1.0001*/), LOL_NEAR_PAD);\n"
 						          "\tconst bool near_ok = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= LOL_NEAR_COORD;\n"
 						          "\tconst lol_u32 list0 = nr.cand;\n"
-						          "\tlol_u32 list = list0;  // rows to evaluate in this round\n"
+						          "\tlol_u64 list = 0xffffffff00000000ull | list0;  // rows to evaluate in this round (0xff ends the list)\n"
+						          "\tbool wide = false;     // the look found five to eight rows: all are evaluated, none remembered\n"
 						          "\tlol_u32 wrow = 0xffu;  // the row that holds `best`, if a row does\n"
 						          "\tlol_u32 nev = 0u;\n"
 						          "\tbool retest = false; // round 0: the last winner is evaluated untested, the others re-tested\n"
 						          "\tbool slow = false;\n"
 						          "\tfor (int round = 0;; ++round) {\n"
 						          "#pragma unroll 1\n"
-						          "\t\tfor (int k = 0; k < 4; ++k) {\n"
-						          "\t\t\tconst lol_u32 row = (list >> (8 * k)) & 0xffu;\n"
+						          "\t\tfor (int k = 0; k < 8; ++k) {\n"
+						          "\t\t\tconst lol_u32 row = (lol_u32)(list >> (8 * k)) & 0xffu;\n"
 						          "\t\t\tif (row == 0xffu)\n\t\t\t\tbreak;\n"
 						          "\t\t\tconst lol_u32* c = lol_run%d + row * LOL_RUN%d_STRIDE;\n"
 						          "\t\t\tif (retest && lol_box_skips(x, y, z, LOL_TF(c[0]), LOL_TF(c[1]), LOL_TF(c[2]), LOL_TF(c[3]), "
 						          "LOL_TF(c[4]), LOL_TF(c[5]), LOL_TF(c[6]), best))\n\t\t\t\tcontinue;\n"
-						          "\t\t\tretest = round == 0;\n"
+						          "\t\t\tretest = round == 0 || wide;\n"
 						          "\t\t\t++nev;\n",
 						          run_no, run_no);
 					}
@@ -1432,24 +1433,24 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "#endif\n"
 						          "\t\t// look at every row again (tests only, out of line)\n"
 						          "\t\tLOL_NEAR_STAT(1, 1);\n"
-						          "\t\tconst lol_u64 seen = lol_near_collect(x, y, z, best);\n"
-						          "\t\tconst lol_u32 nc = (lol_u32)(seen & 0xffffffffull);\n"
-						          "\t\tconst float room = __uint_as_float((lol_u32)(seen >> 32));\n"
-						          "\t\tif (!need && !(room >= 0.f))\n\t\t\tbreak; // a look the ray did not need found more than four rows: what it knew still holds\n"
-						          "\t\tif (!(room >= 0.f)) { // more than four rows cannot be skipped: the plain loop, out of line\n"
+						          "\t\tconst lol_look seen = lol_near_collect(x, y, z, best);\n"
+						          "\t\tif (!need && seen.n > 4u)\n\t\t\tbreak; // a look the ray did not need found more than four rows: what it knew still holds\n"
+						          "\t\tif (seen.n > LOL_NEAR_WIDE) { // more rows cannot be skipped than a look lists: the plain loop, out of line\n"
 						          "\t\t\tslow = true;\n\t\t\tbreak;\n\t\t}\n"
-						          "\t\tnr.cand = nc;\n\t\tnr.room = room;\n"
-						          "\t\t// the new candidates that round 0 did not evaluate\n"
-						          "\t\tlist = 0xffffffffu;\n"
+						          "\t\twide = seen.n > 4u;\n"
+						          "\t\tif (!wide) {\n\t\t\tnr.cand = seen.lo;\n\t\t\tnr.room = seen.room;\n\t\t}\n"
+						          "\t\t// the rows of the look that round 0 did not evaluate\n"
+						          "\t\tconst lol_u64 rows = (lol_u64)seen.lo | ((lol_u64)seen.hi << 32);\n"
+						          "\t\tlist = ~0ull;\n"
 						          "\t\tlol_u32 nl = 0u;\n"
-						          "#pragma unroll\n"
-						          "\t\tfor (int k = 0; k < 4; ++k) {\n"
-						          "\t\t\tconst lol_u32 row = (nc >> (8 * k)) & 0xffu;\n"
-						          "\t\t\tif (row != 0xffu && !lol_near_has(list0, row)) {\n"
-						          "\t\t\t\tlist = (list & ~(0xffu << (8u * nl))) | (row << (8u * nl));\n"
+						          "#pragma unroll 1\n"
+						          "\t\tfor (lol_u32 k = 0; k < seen.n; ++k) {\n"
+						          "\t\t\tconst lol_u32 row = (lol_u32)(rows >> (8u * k)) & 0xffu;\n"
+						          "\t\t\tif (!lol_near_has(list0, row)) {\n"
+						          "\t\t\t\tlist = (list & ~(0xffull << (8u * nl))) | ((lol_u64)row << (8u * nl));\n"
 						          "\t\t\t\t++nl;\n\t\t\t}\n\t\t}\n"
 						          "\t\tif (nl == 0u)\n\t\t\tbreak;\n"
-						          "\t\tretest = false;\n"
+						          "\t\tretest = wide; // (many rows: `best` tightens as they are evaluated, and a row is tested again before it is)\n"
 						          "\t}\n"
 						          "\tLOL_NEAR_STAT(3, nev);\n"
 						          "\tif (slow) {\n"
@@ -1462,7 +1463,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 						          "\t\tnr.cand = (id >= %uu && id < %uu) ? (0xffffff00u | lol_run%d_rowof[id - %uu]) : 0xffffffffu;\n"
 						          "\t\treturn __uint_as_float((lol_u32)r);\n"
 						          "\t}\n"
-						          "\tif (wrow != 0xffu)\n\t\tnr.cand = lol_near_front(nr.cand, wrow);\n"
+						          "\tif (wide) { // nothing is remembered but the winner: the ray looks again at its next point\n"
+						          "\t\tnr.room = -LOL_INF;\n"
+						          "\t\tnr.cand = 0xffffff00u | wrow; // (0xff: no row holds `best`)\n"
+						          "\t} else if (wrow != 0xffu)\n\t\tnr.cand = lol_near_front(nr.cand, wrow);\n"
 						          "\tlol_count_skip((%uu - nev) * %uu);\n"
 						          "\t}\n",
 						          t, t, t, i + 1, j + 1, run_no, i + 1, n, cost);
@@ -1961,13 +1965,14 @@ static const char lol_near_grid_text[] =
 	"#endif // LOL_NEAR_GRID\n";
 
 static const char lol_near_collect_text[] =
-	"// Every row of the pruned table loop against `best`, tests only (lol_kernel.cuh: struct lol_near): the rows\n"
-	"// that cannot be skipped (the first four, one per byte of the low word) and, in the high word, a lower bound of\n"
-	"// min over the skipped rows of  dbox(p) - m1  -- how far the point may move before a skipped row has to be\n"
-	"// looked at again (+INF: none skipped); -1 when more than four rows cannot be skipped (an incomplete look).\n"
-	"__device__ __noinline__ lol_u64 lol_near_collect(const float x, const float y, const float z, const float best) {\n"
+	"// Every row of the pruned table loop against `best`, tests only (lol_kernel.cuh: struct lol_near, lol_look): the\n"
+	"// rows that cannot be skipped (the first eight, one per byte), how many there are, and a lower bound of min over\n"
+	"// the skipped rows of  dbox(p) - m1  -- how far the point may move before a skipped row has to be looked at\n"
+	"// again (+INF: none skipped).\n"
+	"__device__ __noinline__ lol_look lol_near_collect(const float x, const float y, const float z, const float best) {\n"
 	"\tfloat room = LOL_INF;\n"
-	"\tlol_u32 nc = 0xffffffffu, nn = 0u;\n"
+	"\tlol_u64 nc = ~0ull;\n"
+	"\tlol_u32 nn = 0u;\n"
 	"#if LOL_NEAR_GRID\n"
 	"\t{ // the point's cell knows the rows that can matter here, nearest first (lol_grid_build_cell)\n"
 	"\t\tfloat fx = (x - LOL_GRID_X0) * LOL_GRID_IX, fy = (y - LOL_GRID_Y0) * LOL_GRID_IY, fz = (z - LOL_GRID_Z0) * LOL_GRID_IZ;\n"
@@ -2001,14 +2006,11 @@ static const char lol_near_collect_text[] =
 	"\t\t\t\t\t\troom = fminf(room, lol_box_gap(q2, LOL_TF(ct[6])));\n"
 	"\t\t\t\t\t\tcontinue;\n"
 	"\t\t\t\t\t}\n"
-	"\t\t\t\t\tif (nn < 4u)\n"
-	"\t\t\t\t\t\tnc = (nc & ~(0xffu << (8u * nn))) | (i << (8u * nn));\n"
+	"\t\t\t\t\tnc = (nc & ~(0xffull << (8u * nn))) | ((lol_u64)i << (8u * nn)); // (c <= 8: nn < 8 here)\n"
 	"\t\t\t\t\t++nn;\n"
 	"\t\t\t\t}\n"
 	"\t\t\t\tLOL_NEAR_STAT(4 + (nn < 15u ? nn : 15u), 1);\n"
-	"\t\t\t\tif (nn > 4u)\n\t\t\t\t\troom = -1.f;\n"
-	"\t\t\t\telse if (!(room >= 0.f))\n\t\t\t\t\troom = 0.f;\n"
-	"\t\t\t\treturn (lol_u64)nc | ((lol_u64)__float_as_uint(room) << 32);\n"
+	"\t\t\t\treturn lol_look_make(nc, room, nn);\n"
 	"\t\t\t}\n"
 	"\t\t\tLOL_NEAR_STAT(22, 1); // the cell's list ends before a bound above the threshold\n"
 	"\t\t} else\n"
@@ -2032,17 +2034,13 @@ static const char lol_near_collect_text[] =
 	"\t\t\t\troom = fminf(room, lol_box_gap(q2, LOL_TF(ct[6])));\n"
 	"\t\t\t\tcontinue;\n"
 	"\t\t\t}\n"
-	"\t\t\tif (nn < 4u)\n"
-	"\t\t\t\tnc = (nc & ~(0xffu << (8u * nn))) | ((lol_u32)i << (8u * nn));\n"
+	"\t\t\tif (nn < 8u)\n"
+	"\t\t\t\tnc = (nc & ~(0xffull << (8u * nn))) | ((lol_u64)(lol_u32)i << (8u * nn));\n"
 	"\t\t\t++nn;\n"
 	"\t\t}\n"
 	"\t}\n"
 	"\tLOL_NEAR_STAT(4 + (nn < 15u ? nn : 15u), 1);\n"
-	"\tif (nn > 4u) // an incomplete look: the low word holds the first four survivors\n"
-	"\t\troom = -1.f;\n"
-	"\telse if (!(room >= 0.f))\n"
-	"\t\troom = 0.f; // a skipped row right at its margin: no room, but the look is complete\n"
-	"\treturn (lol_u64)nc | ((lol_u64)__float_as_uint(room) << 32);\n"
+	"\treturn lol_look_make(nc, room, nn);\n"
 	"}\n";
 
 /* One pruned table loop of at most 254 rows, and nothing else looped: the shape the per-ray candidate
@@ -2096,7 +2094,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 			            "lol_sdf_ref", prune, 1, smem_ok, &memo, 0, pack, div_ok);
 		if (near) {
 			sb_printf(out, "%s", lol_sdf_slow_text);
-			sb_printf(out, "#define LOL_NEAR_GRID (%d && LOL_GRID_OK)\n", near >= 3);
+			sb_printf(out, "#define LOL_NEAR_GRID (%d && LOL_GRID_OK)\n#define LOL_NEAR_WIDE %du\n", near >= 3, near >= 3 ? 8 : 4);
 			sb_putn(out, lol_near_grid_text, strlen(lol_near_grid_text));
 			sb_putn(out, lol_near_collect_text, strlen(lol_near_collect_text));
 			lol_emit_near = 1;
@@ -2116,7 +2114,7 @@ static void emit_sdf(struct sb* out, const lolb200_scene* s, int loop_threshold,
 		free(fn.p);
 		if (near) {
 			sb_printf(out, "%s", lol_sdf_slow_text);
-			sb_printf(out, "#define LOL_NEAR_GRID (%d && LOL_GRID_OK)\n", near >= 3);
+			sb_printf(out, "#define LOL_NEAR_GRID (%d && LOL_GRID_OK)\n#define LOL_NEAR_WIDE %du\n", near >= 3, near >= 3 ? 8 : 4);
 			sb_putn(out, lol_near_grid_text, strlen(lol_near_grid_text));
 			sb_putn(out, lol_near_collect_text, strlen(lol_near_collect_text));
 			lol_emit_near = 1;
@@ -2471,7 +2469,7 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 		emit_child_materials(&out, s);
 	emit_sdf(&out, s, threshold, o.arith == LOLB200_ARITH_EXACT ? o.guarded_fastpath : 0,
 	         o.prune_bounds, variant == 3, variant != 2 /* variant 2's dynamic smem holds its queues */,
-	         o.pack_pairs, variant == 1 ? (o.near_cache < 0 ? 2 : o.near_cache) : 0,
+	         o.pack_pairs, variant == 1 ? (o.near_cache < 0 ? 3 : o.near_cache) : 0,
 	         (variant == 1 && !(o.shadow_div_pretest != 0)) ? (o.guard_out < 0 ? 3 : (o.guard_out & 3)) : 0);
 	sb_putn(&out, marker, strlen(marker));
 
