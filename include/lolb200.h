@@ -188,8 +188,11 @@ typedef struct lolb200_options {
 	                            its bounding box proves it cannot beat the
 	                            running minimum (exact): always
 	                            in table loops, in straight-line code where a
-	                            sampled estimate says the test pays; 2: every
-	                            straight-line test on; 0: off                   */
+	                            sampled estimate says the test pays -- a box, or
+	                            a ball around one of the object's own sphere
+	                            centres (four instructions instead of sixteen);
+	                            2: every straight-line box test on; 3: as 1, but
+	                            boxes only; 0: off                              */
 	int32_t block_threads;   /* tuning: threads per CTA (multiple of 32);
 	                            0 = the variant's default                       */
 	int32_t min_blocks;      /* tuning: __launch_bounds__ second argument (caps

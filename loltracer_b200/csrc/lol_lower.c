@@ -741,12 +741,78 @@ static void bound_row(const lolb200_scene* s, uint32_t idx, float row[LOL_BOUND_
 	row[6] = nextafterf((float)(M * 1.002 + 1e-6) * 1.004f, INFINITY);
 }
 
+/* A bounding BALL around one of the object's own sphere centres (straight-line objects, emit_sdf_fn).
+ * The box test costs 16 instructions on every evaluation; the squared distance to a sphere's centre is
+ * computed by the object anyway, so a ball around that centre is tested with four.  Every leaf lies within
+ * R of the centre c (sphere: |c_i - c| + r_i; round box: |c_i - c| + |half extents| + r_i), and composites
+ * only shrink or smooth what their leaves span -- dist(object, p) >= (|p - c| - R) - M with the margin M of
+ * bound_node, exactly as for the box.  ball[0..2] = c, ball[3] = 1.004 * (R + M) with the box row's
+ * allowances (lol_ball_skips: u = best * 1.004 + ball[3]).  Returns the leaf's node index, or -1. */
+static void ball_leaves(const lolb200_scene* s, uint32_t idx, const double c[3], double* R, int* ok) {
+	const lolb200_object* o = &s->nodes[idx];
+	double ext;
+	switch (o->type) {
+	case LOLB200_OBJ_SPHERE: ext = fabs((double)o->radius); break;
+	case LOLB200_OBJ_BOX:
+		ext = sqrt((double)o->point2[0] * o->point2[0] + (double)o->point2[1] * o->point2[1] +
+		           (double)o->point2[2] * o->point2[2]) + fabs((double)o->radius);
+		break;
+	case LOLB200_OBJ_PLANE: *ok = 0; return;
+	default:
+		ball_leaves(s, (uint32_t)o->a, c, R, ok);
+		ball_leaves(s, (uint32_t)o->b, c, R, ok);
+		return;
+	}
+	const double d = sqrt(((double)o->point[0] - c[0]) * ((double)o->point[0] - c[0]) +
+	                      ((double)o->point[1] - c[1]) * ((double)o->point[1] - c[1]) +
+	                      ((double)o->point[2] - c[2]) * ((double)o->point[2] - c[2])) + ext;
+	if (!(d <= 1e30))
+		*ok = 0;
+	if (d > *R)
+		*R = d;
+}
+
+static void ball_centres(const lolb200_scene* s, uint32_t root, uint32_t idx, double* bestR, int* best_leaf) {
+	const lolb200_object* o = &s->nodes[idx];
+	if (o->type == LOLB200_OBJ_SPHERE) {
+		const double c[3] = {o->point[0], o->point[1], o->point[2]};
+		double R = 0;
+		int ok = 1;
+		ball_leaves(s, root, c, &R, &ok);
+		if (ok && R < *bestR) {
+			*bestR = R;
+			*best_leaf = (int)idx;
+		}
+	} else if (o->type != LOLB200_OBJ_BOX && o->type != LOLB200_OBJ_PLANE) {
+		ball_centres(s, root, (uint32_t)o->a, bestR, best_leaf);
+		ball_centres(s, root, (uint32_t)o->b, bestR, best_leaf);
+	}
+}
+
+static int ball_row(const lolb200_scene* s, uint32_t idx, float ball[4]) {
+	double lo[3], hi[3], M, R = INFINITY;
+	int leaf = -1;
+	if (s->nodes[idx].type == LOLB200_OBJ_SPHERE || !bound_node(s, idx, lo, hi, &M))
+		return -1; /* (a lone sphere IS its ball: nothing to skip) */
+	ball_centres(s, idx, idx, &R, &leaf);
+	if (leaf < 0)
+		return -1;
+	const lolb200_object* o = &s->nodes[leaf];
+	const double l1 = fabs((double)o->point[0]) + fabs((double)o->point[1]) + fabs((double)o->point[2]);
+	for (int k = 0; k < 3; k++)
+		ball[k] = o->point[k];
+	ball[3] = nextafterf((float)((R * 1.002 + 0.002 * (l1 + 1.0) + 1e-6) + (M * 1.002 + 1e-6)) * 1.004f, INFINITY);
+	return isfinite(ball[3]) ? leaf : -1;
+}
+
 /* ---- two-level pruning: rows sorted along a Morton curve, groups of neighbours ---- */
 /* objects per group; options.prune_group, set by lolb200_lower_cuda for the calling thread */
 static _Thread_local uint32_t lol_group = 8;
 #define LOL_GROUP lol_group
 /* pruned table loops as per-lane work lists (emit_sdf_fn; options.loop_worklist) */
 static _Thread_local int lol_worklist = 0;
+/* options.prune_bounds = 3: straight-line tests are boxes only, no balls (A/B) */
+static _Thread_local int lol_no_balls = 0;
 /* emit_sdf_fn writes lol_sdf_nr: the pruned loop with the per-ray candidate memory (lol_kernel.cuh: struct lol_near) */
 static _Thread_local int lol_emit_near = 0;
 /* Rows that are read with per-lane addresses (work lists, candidate memory) get a stride of 4 x odd
@@ -878,6 +944,12 @@ static int est_box_skips(const float p[3], const float b[7], float best) {
 	return u > 0.f && q[0] * q[0] + q[1] * q[1] + q[2] * q[2] > u * u;
 }
 
+static int est_ball_skips(const float p[3], const float b[4], float best) {
+	const float q[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
+	const float u = best * 1.004f + b[3];
+	return u > 0.f && q[0] * q[0] + q[1] * q[1] + q[2] * q[2] > u * u;
+}
+
 struct est {
 	const lolb200_scene* s;
 	const unsigned char* straight; /* per object: 1 = straight-line code, 2 = straight-line and bounded */
@@ -886,6 +958,8 @@ struct est {
 	uint32_t nb;
 	const float* all;              /* the box around them */
 	unsigned long points, all_fires, *reached, *fires; /* per bounded object */
+	float (*balls)[4];             /* per bounded object: its ball (ball_row), radius slot NaN = none */
+	unsigned long* ball_fires;
 };
 
 /* sdf() at p as the generated code would run it with every test on, counting. */
@@ -903,6 +977,8 @@ static float est_sdf(struct est* e, const float p[3]) {
 		e->reached[q]++;
 		if (est_box_skips(p, e->boxes[k], best))
 			e->fires[q]++;
+		if (e->balls && e->balls[q][3] == e->balls[q][3] && est_ball_skips(p, e->balls[q], best))
+			e->ball_fires[q]++;
 		best = fminf(best, est_node(s, s->objects[k], p));
 	}
 	for (uint32_t k = 0; k < s->n_objects; k++) /* table loops */
@@ -978,13 +1054,30 @@ static void emit_box_test(struct cgen* g, const float box[7], int two) {
  * something with a larger id may have been evaluated before).  own_box: the object
  * is skipped when its bounding box proves it cannot win. */
 static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, const char* sig,
-                                 int two, int tie_aware, const float* own_box, const char* tabs) {
+                                 int two, int tie_aware, const float* own_box, const char* tabs,
+                                 const float* own_ball, int ball_leaf) {
 	char ind[16];
 	snprintf(ind, sizeof ind, "%s\t", tabs);
 	g->indent = ind;
 	g->tmp = 0;
 	sb_printf(body, "%s{ // object %u: %s\n", tabs, k + 1, sig);
-	if (own_box) {
+	if (own_ball && !two) {
+		/* the squared distance to one of the object's own sphere centres: the object computes the very same
+		 * value (same operations, same order: the compiler keeps one copy), so the test costs four instructions */
+		sb_printf(body,
+		          "%s\t// every leaf of the object lies within R of this sphere's centre: dist(object, p) >= |p - c| - R - M >= best\n"
+		          "%s\tconst float bqx = ", tabs, tabs);
+		coord_minus(g, "x", (uint32_t)ball_leaf, F_PX);
+		sb_printf(body, ", bqy = ");
+		coord_minus(g, "y", (uint32_t)ball_leaf, F_PY);
+		sb_printf(body, ", bqz = ");
+		coord_minus(g, "z", (uint32_t)ball_leaf, F_PZ);
+		sb_printf(body, ";\n%s\tif (!lol_ball_skips(lol_dot(bqx, bqy, bqz, bqx, bqy, bqz), ", tabs);
+		cst(g, own_ball[3]);
+		sb_printf(body, ", best)) {\n");
+		snprintf(ind, sizeof ind, "%s\t\t", tabs);
+		own_box = own_ball; /* (closes like a box test below) */
+	} else if (own_box) {
 		sb_printf(body, "%s\t// dist(object, p) >= dbox(p) - M >= best: cannot win\n%s\tif (!", tabs, tabs);
 		emit_box_test(g, own_box, two);
 		sb_printf(body, ") {\n");
@@ -1002,7 +1095,7 @@ static void emit_straight_object(struct sb* body, struct cgen* g, uint32_t k, co
 		          "%sif (a_ < bestA%s) {\n%s\tbestA = a_;\n%s\tbidA = %uu;\n%s}\n"
 		          "%sif (b_ < bestB%s) {\n%s\tbestB = b_;\n%s\tbidB = %uu;\n%s}\n",
 		          ind, t, t, ind, tA, ind, ind, k + 1, ind, ind, tB, ind, ind, k + 1, ind);
-	} else if (g->first_free && g->fast && g->div_ok && !own_box && tabs[1] == '\0')
+	} else if (g->first_free && g->fast && g->div_ok && !own_box && !own_ball && tabs[1] == '\0')
 		/* The first object of the guarded form, outside every test: `best` is still +INF, and the
 		 * result of this function only counts when its range guard passes -- coordinates and every
 		 * scene constant at most 2^60, no NaN -- where an object's distance is finite (sums,
@@ -1196,12 +1289,19 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 		g.first_free = fast && !two;
 		for (uint32_t k = 0; k < no; k++)
 			if (straight[k] == 1)
-				emit_straight_object(&reordered, &g, k, sigs[k], two, 0, NULL, "\t");
+				emit_straight_object(&reordered, &g, k, sigs[k], two, 0, NULL, "\t", NULL, -1);
 		if (nb) {
 			float all[LOL_BOUND_SLOTS];
-			unsigned char* own = calloc(nb, 1);
+			unsigned char* own = calloc(nb, 1); /* per bounded object: 0 no test, 1 its box, 2 its ball (ball_row) */
+			float(*balls)[4] = malloc(sizeof *balls * nb);
+			int* ball_leaf = malloc(sizeof *ball_leaf * nb);
 			int wrap = 0;
 			group_box(boxes, bounded, nb, all);
+			for (uint32_t q = 0; q < nb; q++) {
+				ball_leaf[q] = (two || prune >= 2 || lol_no_balls) ? -1 : ball_row(s, s->objects[bounded[q]], balls[q]);
+				if (ball_leaf[q] < 0)
+					balls[q][0] = balls[q][1] = balls[q][2] = balls[q][3] = NAN;
+			}
 			if (total >= LOL_TEST_PAYS && memo->valid[fast != 0]) {
 				wrap = memo->wrap[fast != 0];
 				memcpy(own, memo->own[fast != 0], nb);
@@ -1209,10 +1309,12 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				/* instructions saved where a test fires (about 1.5 per FLOP of the convention),
 				 * discounted because a warp only saves what ALL its lanes skip, against the
 				 * ~20 instructions the test costs everywhere else */
-				struct est e = {.s = s, .straight = straight, .boxes = boxes, .bounded = bounded, .nb = nb, .all = all};
-				double inside = 0;
+				struct est e = {.s = s, .straight = straight, .boxes = boxes, .bounded = bounded, .nb = nb, .all = all,
+				                .balls = balls};
+				double inside = 0, ball_gain0 = 0;
 				e.reached = calloc(nb, sizeof *e.reached);
 				e.fires = calloc(nb, sizeof *e.fires);
+				e.ball_fires = calloc(nb, sizeof *e.ball_fires);
 				est_march(&e);
 				/* model (calibrated on B200 against the four example scenes): a test is 24
 				 * instructions, reordering costs a tie-aware update (3) per bounded object, and
@@ -1223,20 +1325,41 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 					const double rate = e.reached[q] ? (double)e.fires[q] / (double)e.reached[q] : 0.0;
 					own[q] = nb >= 2 && (prune >= 2 ? node_cost(s, s->objects[bounded[q]]) >= LOL_TEST_PAYS
 					                               : 0.7 * rate * saves > 24.0 + 3.0); /* the test is paid on every evaluation */
-					inside += saves + (own[q] ? 24.0 : 0.0);
+					{
+						/* the ball: 4 instructions + 3 for the reordering; where it fires the object is saved but for
+						 * the squared distance that went in front of the test (about 12 instructions) */
+						const double brate = e.reached[q] ? (double)e.ball_fires[q] / (double)e.reached[q] : 0.0;
+						const double ball_gain = ball_leaf[q] >= 0 ? 0.7 * brate * (saves - 12.0) - (4.0 + 3.0) : -1.0;
+						const double box_gain = 0.7 * rate * saves - (24.0 + 3.0);
+						if (getenv("LOLB200_DEBUG_EST"))
+							fprintf(stderr, "lolb200 estimate: object %u: its ball fires %.1f %% (gain %.1f, its box %.1f)\n",
+							        bounded[q] + 1, brate * 100, ball_gain, box_gain);
+						if (prune == 1 && ball_gain > 0.0 && ball_gain > box_gain && (nb >= 2 || q == 0)) {
+							if (nb >= 2)
+								own[q] = 2;
+							else
+								ball_gain0 = ball_gain; /* one bounded object: against the box around "all" below */
+						}
+					}
+					inside += saves + (own[q] == 1 ? 24.0 : own[q] == 2 ? 4.0 : 0.0);
 					if (getenv("LOLB200_DEBUG_EST"))
-						fprintf(stderr, "lolb200 estimate: object %u: own test fires %.1f %% (saves %.0f) -> %s\n",
-						        bounded[q] + 1, rate * 100, saves, own[q] ? "on" : "off");
+						fprintf(stderr, "lolb200 estimate: object %u: own box test fires %.1f %% (saves %.0f) -> %s\n",
+						        bounded[q] + 1, rate * 100, saves, own[q] == 1 ? "on" : own[q] == 2 ? "its ball instead" : "off");
 				}
 				{
 					const double rate = e.points ? (double)e.all_fires / (double)e.points : 0.0;
 					wrap = prune >= 2 || 0.7 * rate * inside > 24.0 + 3.0 * nb;
+					if (nb == 1 && ball_gain0 > 0.0 && ball_gain0 > 0.7 * rate * inside - (24.0 + 3.0)) {
+						wrap = 0; /* the one bounded object behind its ball instead of its box */
+						own[0] = 2;
+					}
 					if (getenv("LOLB200_DEBUG_EST"))
 						fprintf(stderr, "lolb200 estimate: %lu points, the box around all %u fires %.1f %% (saves %.0f) -> %s\n",
 						        e.points, nb, rate * 100, inside, wrap ? "on" : "off");
 				}
 				free(e.reached);
 				free(e.fires);
+				free(e.ball_fires);
 				memo->valid[fast != 0] = 1;
 				memo->wrap[fast != 0] = wrap;
 				memo->own[fast != 0] = malloc(nb);
@@ -1249,13 +1372,16 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			}
 			for (uint32_t q = 0; q < nb; q++) {
 				const uint32_t k = bounded[q];
-				emit_straight_object(&reordered, &g, k, sigs[k], two, 1, own[q] ? boxes[k] : NULL, wrap ? "\t\t" : "\t");
+				emit_straight_object(&reordered, &g, k, sigs[k], two, 1, own[q] == 1 ? boxes[k] : NULL, wrap ? "\t\t" : "\t",
+				                     own[q] == 2 ? balls[q] : NULL, ball_leaf[q]);
 				any_test |= own[q];
 			}
 			if (wrap)
 				sb_printf(&reordered, "\t} else\n\t\tlol_count_skip(%uu);\n", (total + nb) * (two ? 2u : 1u));
 			any_test |= wrap;
 			free(own);
+			free(balls);
+			free(ball_leaf);
 		}
 		g.out = real_body;
 		if (any_test)
@@ -1689,7 +1815,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			}
 		} else {
 			for (uint32_t k = i; k < j; k++)
-				emit_straight_object(&body, &g, k, sigs[k], two, 0, NULL, "\t");
+				emit_straight_object(&body, &g, k, sigs[k], two, 0, NULL, "\t", NULL, -1);
 		}
 		i = j;
 	}
@@ -2385,6 +2511,9 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	threshold = o.loop_threshold > 0 ? o.loop_threshold : 16;
 	lol_group = o.prune_group > 0 ? (uint32_t)o.prune_group : 8u;
 	lol_worklist = o.loop_worklist < 0 ? 0 : o.loop_worklist; /* measured slower on B200: off */
+	lol_no_balls = o.prune_bounds == 3;
+	if (o.prune_bounds == 3)
+		o.prune_bounds = 1;
 	variant = o.variant;
 	if (variant == 0) /* chosen per scene */
 		variant = (has_table_loop(s, threshold) && !o.prune_bounds) ? 3 : LOLB200_DEFAULT_VARIANT;

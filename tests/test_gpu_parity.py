@@ -591,6 +591,23 @@ def test_straight_line_box_tests_do_not_change_the_frame(name, scenes_dir):
             assert np.array_equal(off[key], on[key]), (variant, key)
         assert np.array_equal(off["dist"].view(np.uint32), on["dist"].view(np.uint32)), variant
         on["renderer"].close()
+    # what the estimate chooses (prune_bounds=1, the default: on scene4 a BALL around one of the blob's own sphere
+    # centres) and the same with boxes only (3), also from cameras the estimate did not march
+    cams = [None, lb.Camera.make([6.0, 3.0, -2.0], [-0.5, -0.3, -1.0], scene.struct.camera.fov),
+            lb.Camera.make([2.0, 2.0, -10.0], [0.1, 0.2, 1.0], scene.struct.camera.fov)]  # the ball's centre on scene4
+    for cam in cams:
+        ref = off if cam is None else _render(lb, scene, w // 2, h // 2, camera=cam, options=lb.Options.default(prune_bounds=0))
+        for prune in (1, 3):
+            on = _render(lb, scene, *(ref["rgba"].shape[::-1]), camera=cam, options=lb.Options.default(prune_bounds=prune))
+            for key in ("rgba", "id", "nprimary", "nshadow"):
+                assert np.array_equal(ref[key], on[key]), (prune, key)
+            da, db = ref["dist"], on["dist"]
+            assert ((da.view(np.uint32) == db.view(np.uint32)) | (np.isnan(da) & np.isnan(db))).all()
+            on["renderer"].close()
+        if cam is not None:
+            ref["renderer"].close()
+    if name == "scene4":
+        assert "lol_ball_skips(lol_dot(" in lb.lower_cuda(scene, lb.Options.default())
     _check(off, ol.port_render(scene, w, h))
     off["renderer"].close()
 

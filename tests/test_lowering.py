@@ -232,7 +232,11 @@ def test_box_tests_are_switched_on_where_they_pay(scenes_dir):
         body = src[src.index("lol_sdf_try(const float x" if "lol_sdf_try(const float x" in src else "lol_sdf(const float x"):]
         return body[:body.index("//@@SCENE@@")]
 
-    assert sdf_text("scene4").count("lol_box_skips(") == 1
+    # scene4's blob sits behind a BALL around one of its own sphere centres (four instructions instead of the
+    # box's sixteen: the squared distance is the sphere's own); with balls off (prune_bounds=3), behind its box
+    assert sdf_text("scene4").count("lol_ball_skips(") == 1 and sdf_text("scene4").count("lol_box_skips(") == 0
+    assert sdf_text("scene4", prune_bounds=3).count("lol_box_skips(") == 1
+    assert sdf_text("scene4", prune_bounds=3).count("lol_ball_skips(") == 0
     assert sdf_text("scene3").count("lol_box_skips(") == 0 and "== best" not in sdf_text("scene3")
     assert sdf_text("scene3") == sdf_text("scene3", prune_bounds=0)
     assert sdf_text("scene3", prune_bounds=2).count("lol_box_skips(") == 1
