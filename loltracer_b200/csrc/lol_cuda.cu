@@ -710,8 +710,11 @@ static int resident_ctas_per_sm(const lolb200_renderer* r, lol_u32 n_chunks) {
 	/* measured on B200, scene4 at 4K: one rank's shard of eight (6.9 tiles per warp at four CTAs per
 	 * SM) 0.300 -> 0.292 ms with three CTAs per SM (tail 30 -> 5 us), two CTAs 0.325 ms; a shard of
 	 * four (13.8 tiles per warp) the same either way; whole frames keep all four */
+	/* round 2, with one-tile chunks and the shorter loops: a shard of four (13.7 chunks per warp) 0.5205 ->
+	 * 0.5026 ms (tail 44 -> 4 us), a shard of two (27 per warp) 0.998 -> 0.990 ms, a whole frame (55 per
+	 * warp) 1.931 -> 1.962 ms: programs with long distance functions switch below 32 chunks per warp */
 	const size_t warps = (size_t)r->sm_count * ctas * (r->threads / 32);
-	if (ctas >= 4 && (size_t)n_chunks < 8 * warps)
+	if (ctas >= 4 && (size_t)n_chunks < (r->long_sdf ? 32 : 8) * warps)
 		return ctas - 1;
 	return ctas;
 }
