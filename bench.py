@@ -347,7 +347,7 @@ def run_reference(args, w, h):
 
 
 # ncu --set full summary of the default scene4 4K launch (tools/ncu_summary.py), committed per round
-NCU_SUMMARY = "r01_v1_final_scene4_4k.txt"
+NCU_SUMMARY = "r02_v1_scene4_4k_ball_test.txt"
 
 
 def _ncu_applies(args, w, h, world):
@@ -360,12 +360,13 @@ def ncu_dram_traffic(args, w, h, world):
     if not _ncu_applies(args, w, h, world):
         return None
     try:
-        total, scale = 0.0, {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total, launches, scale = 0.0, 0, {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(os.path.join(ROOT, "profiles", NCU_SUMMARY)):
+            launches += line.startswith("kernel ")
             if line.strip().startswith("DRAM bytes"):
                 val, unit = line.split("[")[0].split()[-2:]
                 total += float(val) * scale[unit]
-        return total or None
+        return total / max(launches, 1) or None  # per launch: the summary holds one block per captured launch
     except Exception:
         return None
 
