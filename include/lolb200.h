@@ -244,7 +244,7 @@ typedef struct lolb200_options {
 	                            1 = on, 2 = on, and the warp looks at all rows again
 	                            whenever one of its lanes has to (B200, 4K: 1024 spheres
 	                            31.5 -> 29.9 ms), 3 = and a look reads the point's cell
-	                            of a candidate grid (two levels of 32^3 cells, each with
+	                            of a candidate grid (two levels of 64^3 cells, each with
 	                            its eight nearest rows, built on the device when the
 	                            renderer is created) instead of walking every group,
 	                            and up to eight rows are evaluated on the spot before
@@ -257,6 +257,9 @@ typedef struct lolb200_options {
 	                            (exact: same evaluations, same order).  Bits: 1 = the march
 	                            loops, 2 = the four normal taps (one test of their four
 	                            guards); 0 = off, -1 = default (3)                   */
+	int32_t grid_cells;         /* tuning, near_cache = 3: cells per axis of the candidate grid
+	                            (16, 32, 48 or 64); 0 = default (64: 2 x 64^3 cells of 48
+	                            bytes, 25 MB of device memory per renderer)         */
 	int32_t child_materials;    /* EXTENSION, off by default (the reference ignores the
 	                            materials of a composite's children,
 	                            naive_renderer.c:102-112): 1 = a hit on a composite

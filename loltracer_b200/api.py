@@ -76,7 +76,7 @@ class Options(C.Structure):
                 ("prune_group", C.c_int32), ("pack_pairs", C.c_int32), ("share_first_step", C.c_int32),
                 ("shadow_div_pretest", C.c_int32), ("defer_cap_primary", C.c_int32),
                 ("defer_cap_shadow", C.c_int32), ("roll_v1", C.c_int32), ("loop_worklist", C.c_int32),
-                ("near_cache", C.c_int32), ("guard_out", C.c_int32), ("child_materials", C.c_int32)]
+                ("near_cache", C.c_int32), ("guard_out", C.c_int32), ("grid_cells", C.c_int32), ("child_materials", C.c_int32)]
 
     @classmethod
     def default(cls, **kw) -> "Options":

@@ -58,7 +58,7 @@ def test_struct_layouts_match_c(tmp_path):
         seen[name] = (int(size), int(off))
     for name, (cls, last) in pods.items():
         assert seen[name] == (C.sizeof(cls), getattr(cls, last).offset), name
-    assert C.sizeof(api.Options) == 92 and C.sizeof(api.Shard) == 32
+    assert C.sizeof(api.Options) == 96 and C.sizeof(api.Shard) == 32
 
 
 def test_no_cpu_fallback(scenes_dir):

@@ -11,7 +11,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "synthetic"
 w, h = (int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "160x90").split("x"))
 scene = lb.Scene.from_string(scenegen.synthetic_scene_text(csg=name.endswith("csg")))
 near = int(sys.argv[3]) if len(sys.argv) > 3 else -1
-src = lb.lower_cuda(scene, lb.Options.default(variant=1, near_cache=near))
+grid = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+src = lb.lower_cuda(scene, lb.Options.default(variant=1, near_cache=near, grid_cells=grid))
 with tempfile.TemporaryDirectory() as tmp:
     cu = os.path.join(tmp, "p.cpp")
     open(cu, "w").write("#define LOL_NEAR_STATS 1\n" + ol.HOST_SHIM + src + ol.PIPELINE_WRAPPER)
