@@ -1374,8 +1374,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			}
 			for (uint32_t q = 0; q < nb; q++) {
 				const uint32_t k = bounded[q];
-				emit_straight_object(&reordered, &g, k, sigs[k], two, 1, own[q] == 1 ? boxes[k] : NULL, wrap ? "\t\t" : "\t",
-				                     own[q] == 2 ? balls[q] : NULL, ball_leaf[q]);
+				/* (the two-ray form has no ball test: where the single-ray form chose the ball, it keeps the box) */
+				const int ball = own[q] == 2 && ball_leaf[q] >= 0 && !two;
+				emit_straight_object(&reordered, &g, k, sigs[k], two, 1, (own[q] == 1 || (own[q] == 2 && !ball)) ? boxes[k] : NULL,
+				                     wrap ? "\t\t" : "\t", ball ? balls[q] : NULL, ball_leaf[q]);
 				any_test |= own[q];
 			}
 			if (wrap)
