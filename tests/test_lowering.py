@@ -341,3 +341,38 @@ def test_shadow_division_pretest_never_skips_a_needed_division(tmp_path):
     out = subprocess.run([str(exe), "20000000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert " 0 mismatches" in out.stdout
+
+
+def test_the_ball_bound_of_scene4s_blob_is_conservative(scenes_dir):
+    """lol_lower.c: ball_row -- scene4's blob is skipped when |p - c|^2 > (1.004 best + r1)^2 for the centre c of one of
+    its own spheres.  With the floor moved far away the oracle's distance IS the blob's: on 400 000 random points, and on
+    points on the ball's surface, the blob's distance is never below what the ball promises (|p - c| - r1 / 1.004), i.e.
+    a skipped blob could not have won."""
+    import loltracer_b200 as lb
+
+    text = open(os.path.join(scenes_dir, "scene4.lol")).read()
+    src = lb.lower_cuda(lb.Scene.from_string(text), lb.Options.default())
+    body = src[src.index("lol_sdf_try(const float x"):]
+    m = re.search(r"const float bqx = (.*?), bqy = (.*?), bqz = (.*?);\s*if \(!lol_ball_skips\(lol_dot\([^)]*\), LOL_F\(0x([0-9a-f]+)", body)
+    assert m, "scene4's blob is expected behind a ball test"
+
+    def centre(expr, axis):
+        if expr.strip() == axis:
+            return 0.0
+        bits = re.search(r"LOL_F\(0x([0-9a-f]+)", expr).group(1)
+        return float(np.array([int(bits, 16)], np.uint32).view(np.float32)[0])
+
+    c = np.array([centre(m.group(1), "x"), centre(m.group(2), "y"), centre(m.group(3), "z")], np.float64)
+    r1 = float(np.array([int(m.group(4), 16)], np.uint32).view(np.float32)[0])
+    far = lb.Scene.from_string(text.replace("plane { y = -1,", "plane { y = -100000,"))
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(-60, 60, (300000, 3)), rng.uniform(-400, 400, (100000, 3))]).astype(np.float32)
+    d, ids = oracle_sdf(far, pts)
+    assert (ids == 1).all()
+    promise = np.sqrt(((pts.astype(np.float64) - c) ** 2).sum(1)) - r1 / 1.004
+    assert (d.astype(np.float64) >= promise).all(), float((d - promise).min())
+    # the test as the kernel makes it, for running minima of every size: a skipped blob is farther than `best`
+    best = rng.uniform(-3, 40, len(pts))
+    u = best * 1.004 + r1
+    skipped = (u > 0) & (((pts.astype(np.float64) - c) ** 2).sum(1) > u * u)
+    assert skipped.sum() > 10000 and (d[skipped] > best[skipped]).all()

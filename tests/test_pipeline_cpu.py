@@ -299,3 +299,72 @@ def test_candidate_memory_of_pruned_loops_is_exact(kind, tmp_path):
         L = ol.cpu_pipeline(tmp_path, src, f"near_{kind}_cams{near}")
         for cam in cams:
             _same(ol.cpu_pipeline_render(L, lb, scene, 48, 27, camera=cam), ol.port_render(scene, 48, 27, camera=cam, counts=True))
+
+
+GRID_CHECK = r"""
+// The candidate grid's promise, checked point by point: for a point p of a cell, every LISTED row has
+// w <= dbox_row(p) - m1_row, and every row that is NOT listed has rest <= dbox_row(p) - m1_row -- so a
+// row left out of a look cannot fail to be skipped.  Exact side in double precision.
+#include <cstdint>
+extern "C" long grid_check(long n, unsigned long long seed, double* worst) {
+    const long cells = 2l * LOL_GRID_N * LOL_GRID_N * LOL_GRID_N;
+    for (long ci = 0; ci < cells; ++ci) lol_grid_build_cell((int)ci);
+    long bad = 0; *worst = 1e30;
+    auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (double)(seed >> 11) / 9007199254740992.0; };
+    for (long s = 0; s < n; ++s) {
+        const int level = s & 1;
+        const double sc = level ? (double)LOL_GRID_OUTER : 1.0;
+        const double x0 = level ? (double)LOL_GRID_X1 : (double)LOL_GRID_X0, y0 = level ? (double)LOL_GRID_Y1 : (double)LOL_GRID_Y0,
+                     z0 = level ? (double)LOL_GRID_Z1 : (double)LOL_GRID_Z0;
+        const float px = (float)(x0 + rnd() * LOL_GRID_N * (double)LOL_GRID_SX * sc), py = (float)(y0 + rnd() * LOL_GRID_N * (double)LOL_GRID_SY * sc),
+                    pz = (float)(z0 + rnd() * LOL_GRID_N * (double)LOL_GRID_SZ * sc);
+        // the cell as the look computes it (same float arithmetic)
+        const float fx = (px - (level ? LOL_GRID_X1 : LOL_GRID_X0)) * (level ? LOL_GRID_IX / LOL_GRID_OUTER : LOL_GRID_IX);
+        const float fy = (py - (level ? LOL_GRID_Y1 : LOL_GRID_Y0)) * (level ? LOL_GRID_IY / LOL_GRID_OUTER : LOL_GRID_IY);
+        const float fz = (pz - (level ? LOL_GRID_Z1 : LOL_GRID_Z0)) * (level ? LOL_GRID_IZ / LOL_GRID_OUTER : LOL_GRID_IZ);
+        const float top = (float)LOL_GRID_N;
+        if (!(fx >= 0.f && fx < top && fy >= 0.f && fy < top && fz >= 0.f && fz < top)) continue;
+        const lol_cell& c = lol_grid[level * LOL_GRID_N * LOL_GRID_N * LOL_GRID_N + ((int)fz * LOL_GRID_N + (int)fy) * LOL_GRID_N + (int)fx];
+        for (int i = 0; i < LOL_RUN0_ROWS; ++i) {
+            const lol_u32* ct = lol_tables + lol_run0_offset + i * LOL_RUN0_STRIDE;
+            const double qx = std::fmax(std::fabs((double)px - LOL_TF(ct[0])) - LOL_TF(ct[3]), 0.0);
+            const double qy = std::fmax(std::fabs((double)py - LOL_TF(ct[1])) - LOL_TF(ct[4]), 0.0);
+            const double qz = std::fmax(std::fabs((double)pz - LOL_TF(ct[2])) - LOL_TF(ct[5]), 0.0);
+            const double gap = std::sqrt(qx * qx + qy * qy + qz * qz) - (double)LOL_TF(ct[6]);
+            double bound = c.rest;
+            for (int k = 0; k < 8; ++k)
+                if (((c.rows[k >> 2] >> (8 * (k & 3))) & 0xffu) == (lol_u32)i) bound = c.w[k];
+            if (gap - bound < *worst) *worst = gap - bound;
+            bad += !(bound <= gap);
+        }
+        for (int k = 1; k < 8; ++k) bad += !(c.w[k - 1] <= c.w[k]);   // ascending
+        bad += !(c.w[7] <= c.rest);
+    }
+    return bad;
+}
+"""
+
+
+@pytest.mark.parametrize("kind,cells", [("synthetic", 32), ("synthetic", 64), ("crowd", 16), ("sparse", 48)])
+def test_candidate_grid_bounds_are_conservative(kind, cells, tmp_path):
+    """lol_grid_build_cell (generated; on the GPU a one-off kernel runs it): 200 000 random points in both
+    levels of the grid, every row against its cell's bound in double precision -- no row's true
+    dbox(p) - m1 may be below what its cell promises, lists ascend, and the slack is small but positive."""
+    import ctypes as C
+    import pathlib
+    import subprocess
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_string(_near_scene(kind))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1, loop_threshold=8, near_cache=3, grid_cells=cells))
+    assert "#define LOL_NEAR_GRID (1 &&" in src and f"#define LOL_GRID_N {cells}" in src
+    cu = pathlib.Path(tmp_path) / "grid.cpp"
+    cu.write_text(ol.HOST_SHIM + src + GRID_CHECK)
+    so = pathlib.Path(tmp_path) / "grid.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cu)])
+    L = C.CDLL(str(so))
+    L.grid_check.restype = C.c_long
+    L.grid_check.argtypes = [C.c_long, C.c_ulonglong, C.POINTER(C.c_double)]
+    worst = C.c_double()
+    assert L.grid_check(200000, 12345, C.byref(worst)) == 0, worst.value
+    assert 0.0 <= worst.value < 0.05, worst.value
