@@ -192,7 +192,9 @@ typedef struct lolb200_options {
 	                            a ball around one of the object's own sphere
 	                            centres (four instructions instead of sixteen);
 	                            2: every straight-line box test on; 3: as 1, but
-	                            boxes only; 0: off                              */
+	                            boxes only; 4: as 2, with the ball in place of
+	                            the box wherever an object has one (tests);
+	                            0: off                                          */
 	int32_t block_threads;   /* tuning: threads per CTA (multiple of 32);
 	                            0 = the variant's default                       */
 	int32_t min_blocks;      /* tuning: __launch_bounds__ second argument (caps

@@ -815,6 +815,8 @@ static _Thread_local int lol_worklist = 0;
 static _Thread_local int lol_grid_n = 64;
 /* options.prune_bounds = 3: straight-line tests are boxes only, no balls (A/B) */
 static _Thread_local int lol_no_balls = 0;
+/* options.prune_bounds = 4: as 2, and every straight-line object that has a ball is tested with it (tests) */
+static _Thread_local int lol_force_balls = 0;
 /* emit_sdf_fn writes lol_sdf_nr: the pruned loop with the per-ray candidate memory (lol_kernel.cuh: struct lol_near) */
 static _Thread_local int lol_emit_near = 0;
 /* Rows that are read with per-lane addresses (work lists, candidate memory) get a stride of 4 x odd
@@ -1300,7 +1302,7 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 			int wrap = 0;
 			group_box(boxes, bounded, nb, all);
 			for (uint32_t q = 0; q < nb; q++) {
-				ball_leaf[q] = (two || prune >= 2 || lol_no_balls) ? -1 : ball_row(s, s->objects[bounded[q]], balls[q]);
+				ball_leaf[q] = (two || (prune >= 2 && !lol_force_balls) || lol_no_balls) ? -1 : ball_row(s, s->objects[bounded[q]], balls[q]);
 				if (ball_leaf[q] < 0)
 					balls[q][0] = balls[q][1] = balls[q][2] = balls[q][3] = NAN;
 			}
@@ -1367,6 +1369,10 @@ static void emit_sdf_fn(struct sb* out, struct sb* tables_out, const lolb200_sce
 				memo->own[fast != 0] = malloc(nb);
 				memcpy(memo->own[fast != 0], own, nb);
 			}
+			if (lol_force_balls) /* every object that has a ball behind it, whatever an estimate would say */
+				for (uint32_t q = 0; q < nb; q++)
+					if (ball_leaf[q] >= 0)
+						own[q] = 2;
 			if (wrap) {
 				sb_printf(&reordered, "\t// none of the %u bounded objects can win: dist >= dbox(p) - M >= best\n\tif (!", nb);
 				emit_box_test(&g, all, two);
@@ -2086,6 +2092,15 @@ static const char lol_near_grid_text[] =
 	"\tc.pad = 0u;\n"
 	"\tlol_grid[cell] = c;\n"
 	"}\n"
+	"#ifdef LOL_HOST_SHIM\n"
+	"// host builds of the pipeline (the CPU test suite) build a cell when a look first reads it\n"
+	"static unsigned char lol_grid_built[2 * LOL_GRID_N * LOL_GRID_N * LOL_GRID_N];\n"
+	"static inline const lol_cell& lol_grid_at(const int cell) {\n"
+	"\tif (!lol_grid_built[cell]) {\n\t\tlol_grid_build_cell(cell);\n\t\tlol_grid_built[cell] = 1;\n\t}\n"
+	"\treturn lol_grid[cell];\n}\n"
+	"#else\n"
+	"#define lol_grid_at(cell) lol_grid[cell]\n"
+	"#endif\n"
 	"#ifndef LOL_HOST_SHIM\n"
 	"extern \"C\" __global__ void lol_grid_build() {\n"
 	"\tconst int ci = (int)(blockIdx.x * blockDim.x + threadIdx.x);\n"
@@ -2115,7 +2130,7 @@ static const char lol_near_collect_text[] =
 	"\t\t\tbase = LOL_GRID_N * LOL_GRID_N * LOL_GRID_N;\n"
 	"\t\t}\n"
 	"\t\tif (fx >= 0.f && fx < top && fy >= 0.f && fy < top && fz >= 0.f && fz < top) { // (a NaN is outside)\n"
-	"\t\t\tconst lol_cell cell = lol_grid[base + ((int)fz * LOL_GRID_N + (int)fy) * LOL_GRID_N + (int)fx];\n"
+	"\t\t\tconst lol_cell cell = lol_grid_at(base + ((int)fz * LOL_GRID_N + (int)fy) * LOL_GRID_N + (int)fx);\n"
 	"\t\t\tconst float thr = fabsf(best) * LOL_F(0x3f808366 /*1.00401*/); // a row with w > 1.004 |best| is skipped wherever the point is in the cell\n"
 	"\t\t\tfloat next = cell.rest;\n"
 	"\t\t\tint c = 0;\n"
@@ -2516,6 +2531,9 @@ char* lolb200_lower_cuda(const lolb200_scene* s, const lolb200_options* opt, siz
 	lol_group = o.prune_group > 0 ? (uint32_t)o.prune_group : 8u;
 	lol_worklist = o.loop_worklist < 0 ? 0 : o.loop_worklist; /* measured slower on B200: off */
 	lol_no_balls = o.prune_bounds == 3;
+	lol_force_balls = o.prune_bounds == 4;
+	if (o.prune_bounds == 4)
+		o.prune_bounds = 2;
 	/* measured on B200, 1024 spheres at 4K: 16 cells per axis 25.31 ms, 32: 24.33, 48: 24.00, 64: 23.75 (25 MB of cells) */
 	lol_grid_n = (o.grid_cells == 16 || o.grid_cells == 32 || o.grid_cells == 48 || o.grid_cells == 64) ? o.grid_cells : 64;
 	if (o.prune_bounds == 3)

@@ -32,6 +32,7 @@ OPTIONS = {
     "no_skips": dict(skip_black_miss=0, cull_backfacing=0, shadow_early_out=0, share_first_step=0),
     "everything_on": dict(guarded_fastpath=2, pack_pairs=2, share_first_step=2, shadow_div_pretest=1, prune_bounds=2),
     "ieee_forms": dict(guarded_fastpath=0, prune_bounds=0),
+    "forced_balls": dict(guarded_fastpath=2, prune_bounds=4),
     "guard_inside_the_loops": dict(guard_out=0, guarded_fastpath=2),
     "forced_loops": dict(loop_threshold=2, guarded_fastpath=2, share_first_step=2),
 }
@@ -115,7 +116,9 @@ def test_host_compiled_pipeline_on_random_scenes(seed, tmp_path):
     w, h = 48, 27
     want = ol.port_render(scene, w, h, counts=True)
     for tag, kw in (("s", dict(guarded_fastpath=2, pack_pairs=2, share_first_step=2, shadow_div_pretest=1)),
-                    ("l", dict(guarded_fastpath=2, loop_threshold=2, prune_bounds=2))):
+                    ("l", dict(guarded_fastpath=2, loop_threshold=2, prune_bounds=2)),
+                    # every object that has one behind its bounding ball, the guard's fall-back outside the loops
+                    ("b", dict(guarded_fastpath=2, loop_threshold=99, prune_bounds=4))):
         src = lb.lower_cuda(scene, lb.Options.default(variant=1, **kw))
         L = ol.cpu_pipeline(tmp_path, src, f"fz{seed}{tag}")
         _same(ol.cpu_pipeline_render(L, lb, scene, w, h), want)
