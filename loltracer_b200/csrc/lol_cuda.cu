@@ -1172,6 +1172,9 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 	/* fewer slabs as the shard shrinks: with eight ranks the copy is a quarter of
 	 * the kernel and every slab costs its host thread API calls */
 	size_t slabs = LOL_MAX_SLABS / world >= 2 ? LOL_MAX_SLABS / world : 2;
+	if (const char* e = getenv("LOLB200_SHARD_SLABS")) /* A/B: forces the slab count of a shard */
+		if (atoi(e) > 0 && atoi(e) <= LOL_MAX_SLABS)
+			slabs = (size_t)atoi(e);
 	if (local_bands < slabs * 16)
 		slabs = local_bands / 16 ? local_bands / 16 : 1;
 	size_t* begin = r->pending.begin;
