@@ -1173,7 +1173,7 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 	 * the kernel and every slab costs its host thread API calls.  Measured on B200 (scene4 4K, e2e per frame):
 	 * two ranks 4 slabs 1.150 ms against 1.217 with 2 and 1.191 with 8; four ranks 4 slabs 0.6385 against 0.6673
 	 * with 2 and 0.6678 with 3 (round 2; eight ranks keep the 2 they were tuned with) */
-	size_t slabs = world <= 4 ? 4 : 2;
+	size_t slabs = world <= 1 ? LOL_MAX_SLABS : world <= 4 ? 4 : 2;
 	if (const char* e = getenv("LOLB200_SHARD_SLABS")) /* A/B: forces the slab count of a shard */
 		if (atoi(e) > 0 && atoi(e) <= LOL_MAX_SLABS)
 			slabs = (size_t)atoi(e);
