@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
     ap.add_argument("--opts", default="", help="extra lowering options, k=v,k=v (A/B runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-slabs", default="", help="N > 1: also time the e2e path with these slab counts per shard "
+                    "(LOLB200_SHARD_SLABS), e.g. 2,4 -> extra key e2e_slab_sweep (A/B inside one run)")
     ap.add_argument("--no-extras", action="store_true", help="skip per_config / moving camera / in-process group")
     ap.add_argument("--all-scenes", action="store_true",
                     help="also time the other example scenes at this size (extra key per_scene)")
@@ -879,6 +881,19 @@ def main():
     job.sync_all()
     e2e_ms = job.max_over_ranks([(time.perf_counter() - t0) / K * 1e3])[0]
     e2e_value = w * h / (e2e_ms * 1e-3) / 1e6
+    e2e_sweep = {}
+    if shared is not None and args.e2e_slabs:
+        for v in args.e2e_slabs.split(","):
+            os.environ["LOLB200_SHARD_SLABS"] = v.strip()
+            for _ in range(3):
+                e2e_step()
+            job.sync_all()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                e2e_step()
+            job.sync_all()
+            e2e_sweep[v.strip()] = job.max_over_ranks([(time.perf_counter() - t0) / K * 1e3])[0]
+        os.environ.pop("LOLB200_SHARD_SLABS", None)
     if shared is not None:
         if rank == 0:
             e2e_verified = bool(np.array_equal(np.asarray(shared), frame.cpu().numpy().view(np.uint32)))
@@ -981,7 +996,8 @@ def main():
                          "shared-memory host frame; completion through frame numbers in a shared page"
                          if args.e2e_path == "host-shards" else
                          "frame gathered on rank 0 over NVLink, then one D2H copy from rank 0"),
-                "host_frame_equals_single_gpu": e2e_verified},
+                "host_frame_equals_single_gpu": e2e_verified,
+                **({"slab_sweep_ms_per_frame": e2e_sweep} if e2e_sweep else {})},
         "gpu_launches": n_launches,
         "sharded_frame_equals_single_gpu": verified,
         "roofline": roofline,

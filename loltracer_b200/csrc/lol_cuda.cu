@@ -1172,8 +1172,9 @@ static int host_shard_enqueue(lolb200_renderer* r, const lolb200_camera* cam, in
 	/* fewer slabs as the shard shrinks: with eight ranks the copy is a quarter of
 	 * the kernel and every slab costs its host thread API calls.  Measured on B200 (scene4 4K, e2e per frame):
 	 * two ranks 4 slabs 1.150 ms against 1.217 with 2 and 1.191 with 8; four ranks 4 slabs 0.6385 against 0.6673
-	 * with 2 and 0.6678 with 3 (round 2; eight ranks keep the 2 they were tuned with) */
-	size_t slabs = world <= 1 ? LOL_MAX_SLABS : world <= 4 ? 4 : 2;
+	 * with 2 and 0.6678 with 3; eight ranks 4 slabs 0.4404 against 0.4511 with 2 and 0.4460 with 3, timed inside
+	 * one run (bench.py --e2e-slabs) */
+	size_t slabs = world <= 1 ? LOL_MAX_SLABS : 4;
 	if (const char* e = getenv("LOLB200_SHARD_SLABS")) /* A/B: forces the slab count of a shard */
 		if (atoi(e) > 0 && atoi(e) <= LOL_MAX_SLABS)
 			slabs = (size_t)atoi(e);
