@@ -54,6 +54,19 @@ def test_host_compiled_pipeline_equals_oracle(name, opts, scenes_dir, tmp_path):
 
 
 @pytest.mark.parametrize("name", EXAMPLES)
+def test_host_compiled_pipeline_at_the_reference_window_size(name, scenes_dir, tmp_path):
+    """BASELINE config C1's size (main.c:136-137, 320x240) through the default program of every example --
+    on scene4 that is the ball test, the guard's fall-back outside the march loops and the unconditional first
+    object -- against the oracle: distance, id, step counts and RGB of all 76 800 pixels, exact."""
+    import loltracer_b200 as lb
+
+    scene = lb.Scene.from_file(os.path.join(scenes_dir, name + ".lol"))
+    src = lb.lower_cuda(scene, lb.Options.default(variant=1))
+    L = ol.cpu_pipeline(tmp_path, src, f"{name}_window")
+    _same(ol.cpu_pipeline_render(L, lb, scene, 320, 240), ol.port_render(scene, 320, 240, counts=True))
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
 @pytest.mark.parametrize("loops", [0, 2])
 def test_host_compiled_two_ray_pipeline_equals_oracle(name, loops, scenes_dir, tmp_path):
     """Variant 3 (lol_shade_pair: two horizontally adjacent pixels per call, a finished ray waiting for
