@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LOLB200_ABI_VERSION 2
+#define LOLB200_ABI_VERSION 3 /* 3: lolb200_options grew (guard_out, grid_cells) */
 
 enum {
 	LOLB200_OK = 0,

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(raw, s), f"{s} declared in lolb200.h but not exported"
-    assert lb.lib().lolb200_abi_version() == 2
+    assert lb.lib().lolb200_abi_version() == 3
 
 
 def test_bindings_cover_the_header():
